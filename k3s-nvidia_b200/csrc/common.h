@@ -1,0 +1,66 @@
+// Internal helpers shared by the translation units of libb200probe.so.  Not part of the ABI.
+#pragma once
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include "../../include/b200probe.h"
+
+namespace b200 {
+
+// thread-local detailed error text (b200probe_last_error)
+void set_error(const char* fmt, ...) __attribute__((format(printf, 1, 2)));
+const char* get_error();
+
+// NVML index -> CUDA ordinal (by UUID); initialises CUDA lazily.  Returns a b200probe rc.
+int cuda_ordinal_of(int nvml_idx, int* ordinal);
+// Make sure CUDA is usable and `ordinal` is an sm_100 device; caches per-device properties.
+struct DevProps {
+    int  sms;
+    int  l2_bytes;
+    int  smem_optin;
+    int  cc_major, cc_minor;
+};
+int device_props(int ordinal, DevProps* out);
+
+inline int cuda_rc(int cuda_err) { return cuda_err == 0 ? 0 : B200PROBE_CUDA_BASE + cuda_err; }
+
+}  // namespace b200
+
+#define B200_CUDA_TRY(expr)                                                                   \
+    do {                                                                                      \
+        cudaError_t e__ = (expr);                                                             \
+        if (e__ != cudaSuccess) {                                                             \
+            b200::set_error("%s:%d %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(e__)); \
+            return b200::cuda_rc((int)e__);                                                   \
+        }                                                                                     \
+    } while (0)
+
+// ---- data pattern, shared host/device (header-only so the kernels inline it) -----------------
+#if defined(__CUDACC__)
+#define B200_HD __host__ __device__ __forceinline__
+#else
+#define B200_HD inline
+#endif
+B200_HD uint32_t b200_pattern_word(uint64_t i, uint32_t seed) {
+    return ((uint32_t)i * 2654435761u) ^ seed ^ (uint32_t)(i >> 32);
+}
+// splitmix-style 32-bit finaliser (GEMM operand generator)
+B200_HD uint32_t b200_mix32(uint32_t x) {
+    x ^= x >> 16; x *= 0x7feb352du; x ^= x >> 15; x *= 0x846ca68bu; x ^= x >> 16;
+    return x;
+}
+// bf16 operand element e of matrix `which`: k/128 with k an integer in [-128,127], exactly
+// representable in bf16 (8 significant bits), so the CPU oracle and the device agree on the bits.
+B200_HD uint16_t b200_gemm_elem_bits(uint64_t e, uint32_t seed, int which) {
+    uint32_t h = b200_mix32((uint32_t)e * 0x9E3779B1u ^ b200_mix32(seed + 0x51ED27u * (uint32_t)(which + 1)) ^ (uint32_t)(e >> 32));
+    int k = (int)(h & 0xFF) - 128;                    // [-128,127]
+    float f = (float)k * (1.0f / 128.0f);             // exact
+    uint32_t u;
+#if defined(__CUDA_ARCH__)
+    u = __float_as_uint(f);
+#else
+    memcpy(&u, &f, 4);
+#endif
+    return (uint16_t)(u >> 16);                       // exact: low 16 mantissa bits are zero
+}

@@ -1,0 +1,640 @@
+// HBM bandwidth sweep kernels for sm_100a (no reference counterpart —
+// the reference plugin's health path, /root/reference/README.md:116, moves no GPU bytes).
+//
+// Two families, same data contract (include/b200probe.h):
+//   TMA ring  : every warp owns a ring of shared-memory stages.  global->shared moves are
+//               cp.async.bulk (SASS UBLKCP) completing on an mbarrier; shared->global moves are
+//               cp.async.bulk bulk_group stores.  The copy path never touches registers: one lane
+//               per warp drives the TMA engine, so bytes in flight are bounded by shared memory
+//               (up to ~200 KB/SM), not by registers or LSU queues.
+//   direct    : LDG.128 / STG.128 grid-stride with 8 independent requests per thread.
+//
+// Roofline: HBM bound.  Algorithmic bytes per launch: read N, write N, copy 2N.
+#include <cuda_runtime.h>
+#include <pthread.h>
+
+#include <algorithm>
+#include <vector>
+
+#include "common.h"
+
+namespace {
+
+// ------------------------------------------------------------------------------------------------
+// PTX wrappers
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(bar), "r"(parity)
+            : "memory");
+    } while (!done);
+}
+// global -> shared, completes (complete_tx) on the mbarrier; evict-first L2 policy: streamed once.
+__device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void* src, uint32_t bytes, uint32_t bar, uint64_t policy) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(dst_smem),
+        "l"(src), "r"(bytes), "r"(bar), "l"(policy)
+        : "memory");
+}
+// shared -> global, tracked by the thread's bulk async-group
+__device__ __forceinline__ void bulk_s2g(void* dst, uint32_t src_smem, uint32_t bytes, uint64_t policy) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;" ::"l"(dst), "r"(src_smem), "r"(bytes),
+                 "l"(policy)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read_dyn(int n) {   // n outstanding groups may keep reading
+    switch (n) {
+        case 0: bulk_wait_read<0>(); break;
+        case 1: bulk_wait_read<1>(); break;
+        case 2: bulk_wait_read<2>(); break;
+        case 3: bulk_wait_read<3>(); break;
+        case 4: bulk_wait_read<4>(); break;
+        case 5: bulk_wait_read<5>(); break;
+        case 6: bulk_wait_read<6>(); break;
+        default: bulk_wait_read<7>(); break;
+    }
+}
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ uint64_t policy_evict_first() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+
+constexpr int kMaxWarps = 8;
+constexpr int kMaxStages = 8;
+
+struct RingArgs {
+    const uint8_t* src;
+    uint8_t* dst;
+    uint64_t bytes;            // multiple of 4
+    uint32_t seed;
+    uint32_t stage_bytes;      // multiple of 512
+    uint32_t stages;           // 2..kMaxStages
+    unsigned long long* partials;   // [0] sum64, [1] xor (read mode)
+};
+
+__device__ __forceinline__ void accum16(const uint4& v, unsigned long long& sum, uint32_t& x) {
+    sum += (unsigned long long)v.x + v.y;
+    sum += (unsigned long long)v.z + v.w;
+    x ^= v.x ^ v.y ^ v.z ^ v.w;
+}
+
+__device__ __forceinline__ void warp_publish(unsigned long long sum, uint32_t x, unsigned long long* partials) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        sum += __shfl_xor_sync(0xffffffffu, sum, o);
+        x ^= __shfl_xor_sync(0xffffffffu, x, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicAdd(partials, sum);
+        atomicXor(partials + 1, (unsigned long long)x);
+    }
+}
+
+// The <16-byte (word-granular) tail that bulk copies cannot carry; one thread of the grid.
+__device__ __forceinline__ void tail_words(int mode, const RingArgs& a, uint64_t bulk_bytes) {
+    if (blockIdx.x != 0 || threadIdx.x != 0) return;
+    unsigned long long sum = 0;
+    uint32_t x = 0;
+    for (uint64_t off = bulk_bytes; off < a.bytes; off += 4) {
+        if (mode == B200PROBE_HBM_READ) {
+            uint32_t w = *reinterpret_cast<const uint32_t*>(a.src + off);
+            sum += w; x ^= w;
+        } else if (mode == B200PROBE_HBM_WRITE) {
+            *reinterpret_cast<uint32_t*>(a.dst + off) = b200_pattern_word(off >> 2, a.seed);
+        } else {
+            *reinterpret_cast<uint32_t*>(a.dst + off) = *reinterpret_cast<const uint32_t*>(a.src + off);
+        }
+    }
+    if (mode == B200PROBE_HBM_READ && bulk_bytes < a.bytes) {
+        atomicAdd(a.partials, sum);
+        atomicXor(a.partials + 1, (unsigned long long)x);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// TMA ring kernel.  One ring per warp; chunk c of the buffer goes to worker c % nworkers.
+// ------------------------------------------------------------------------------------------------
+template <int MODE>
+__global__ void __launch_bounds__(kMaxWarps * 32) hbm_ring_kernel(RingArgs a) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    __shared__ __align__(8) uint64_t full_bar[kMaxWarps * kMaxStages];
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nwarps = blockDim.x >> 5;
+    const uint32_t S = a.stages, SB = a.stage_bytes;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < kMaxWarps * kMaxStages; ++i) mbar_init(smem_u32(&full_bar[i]), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    const uint64_t bulk_bytes = a.bytes & ~15ull;
+    const uint64_t nchunks = (bulk_bytes + SB - 1) / SB;
+    const uint64_t worker = (uint64_t)blockIdx.x * nwarps + warp;
+    const uint64_t nworkers = (uint64_t)gridDim.x * nwarps;
+    const uint64_t n_my = worker < nchunks ? (nchunks - worker + nworkers - 1) / nworkers : 0;
+
+    const uint32_t ring = smem_u32(smem) + warp * S * SB;
+    uint8_t* ring_ptr = smem + (size_t)warp * S * SB;
+    const uint32_t bar0 = smem_u32(&full_bar[warp * kMaxStages]);
+    const uint64_t pol = policy_evict_first();
+
+    auto chunk_off = [&](uint64_t k) { return (worker + k * nworkers) * (uint64_t)SB; };
+    auto chunk_len = [&](uint64_t k) { uint64_t o = chunk_off(k); return (uint32_t)min((uint64_t)SB, bulk_bytes - o); };
+    // producer cursor (stage ps) and consumer cursor (stage cs, parity cph) advance without div/mod
+    uint32_t ps = 0, cs = 0, cph = 0;
+    uint64_t issued = 0;
+    auto load_next = [&]() {
+        const uint32_t len = chunk_len(issued);
+        mbar_expect_tx(bar0 + ps * 8, len);
+        bulk_g2s(ring + ps * SB, a.src + chunk_off(issued), len, bar0 + ps * 8, pol);
+        ++issued;
+        if (++ps == S) ps = 0;
+    };
+    auto advance = [&]() { if (++cs == S) { cs = 0; cph ^= 1; } };
+
+    if (MODE == B200PROBE_HBM_COPY) {
+        if (lane == 0 && n_my > 0) {
+            const uint64_t ahead = min((uint64_t)(S - 1), n_my);
+            while (issued < ahead) load_next();
+            for (uint64_t k = 0; k < n_my; ++k) {
+                mbar_wait(bar0 + cs * 8, cph);
+                bulk_s2g(a.dst + chunk_off(k), ring + cs * SB, chunk_len(k), pol);
+                bulk_commit();
+                if (issued < n_my) {
+                    bulk_wait_read<1>();       // store k-1 has drained its stage, which the next load reuses
+                    load_next();
+                }
+                advance();
+            }
+            bulk_wait_all();
+        }
+    } else if (MODE == B200PROBE_HBM_READ) {
+        unsigned long long sum = 0;
+        uint32_t x = 0;
+        if (lane == 0) {
+            const uint64_t ahead = min((uint64_t)S, n_my);
+            while (issued < ahead) load_next();
+        }
+        for (uint64_t k = 0; k < n_my; ++k) {
+            mbar_wait(bar0 + cs * 8, cph);
+            const uint4* st = reinterpret_cast<const uint4*>(ring_ptr + (size_t)cs * SB);
+            const uint32_t nvec = chunk_len(k) >> 4;
+            uint32_t i = lane;
+            for (; i + 96 < nvec; i += 128) {
+                uint4 v0 = st[i], v1 = st[i + 32], v2 = st[i + 64], v3 = st[i + 96];
+                accum16(v0, sum, x); accum16(v1, sum, x); accum16(v2, sum, x); accum16(v3, sum, x);
+            }
+            for (; i < nvec; i += 32) accum16(st[i], sum, x);
+            __syncwarp();
+            // lane 0 is the only producer: its `issued` counts k+S loads here, stage ps == cs
+            if (lane == 0 && k + S < n_my) load_next();
+            advance();
+        }
+        warp_publish(sum, x, a.partials);
+    } else {   // WRITE: generate the pattern into the stage, then bulk-store it
+        for (uint64_t k = 0; k < n_my; ++k) {
+            if (k >= S) {
+                if (lane == 0) bulk_wait_read_dyn((int)S - 1);   // store k-S no longer reads stage cs
+                __syncwarp();
+            }
+            uint4* st = reinterpret_cast<uint4*>(ring_ptr + (size_t)cs * SB);
+            const uint32_t nvec = chunk_len(k) >> 4;
+            const uint64_t w0 = chunk_off(k) >> 2;
+#pragma unroll 4
+            for (uint32_t i = lane; i < nvec; i += 32) {
+                uint64_t w = w0 + (uint64_t)i * 4;
+                st[i] = make_uint4(b200_pattern_word(w, a.seed), b200_pattern_word(w + 1, a.seed),
+                                   b200_pattern_word(w + 2, a.seed), b200_pattern_word(w + 3, a.seed));
+            }
+            fence_proxy_async_smem();          // generic-proxy writes -> visible to the async proxy
+            __syncwarp();
+            if (lane == 0) {
+                bulk_s2g(a.dst + chunk_off(k), ring + cs * SB, chunk_len(k), pol);
+                bulk_commit();
+            }
+            advance();
+        }
+        if (lane == 0) bulk_wait_all();
+    }
+    tail_words(MODE, a, bulk_bytes);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Direct LDG.128 / STG.128 kernels: 8 independent 16-byte requests per thread per iteration.
+// ------------------------------------------------------------------------------------------------
+constexpr int kUnroll = 8;
+
+template <int MODE>
+__global__ void __launch_bounds__(512) hbm_direct_kernel(RingArgs a) {
+    const uint64_t nvec = a.bytes >> 4;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    const uint64_t tid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint4* __restrict__ src = reinterpret_cast<const uint4*>(a.src);
+    uint4* __restrict__ dst = reinterpret_cast<uint4*>(a.dst);
+    unsigned long long sum = 0;
+    uint32_t x = 0;
+
+    uint64_t i = tid;
+    for (; i + (kUnroll - 1) * stride < nvec; i += kUnroll * stride) {
+        uint4 v[kUnroll];
+        if (MODE != B200PROBE_HBM_WRITE) {
+#pragma unroll
+            for (int j = 0; j < kUnroll; ++j) v[j] = __ldcs(src + i + j * stride);
+        } else {
+#pragma unroll
+            for (int j = 0; j < kUnroll; ++j) {
+                uint64_t w = (i + j * stride) * 4;
+                v[j] = make_uint4(b200_pattern_word(w, a.seed), b200_pattern_word(w + 1, a.seed), b200_pattern_word(w + 2, a.seed),
+                                  b200_pattern_word(w + 3, a.seed));
+            }
+        }
+        if (MODE == B200PROBE_HBM_READ) {
+#pragma unroll
+            for (int j = 0; j < kUnroll; ++j) accum16(v[j], sum, x);
+        } else {
+#pragma unroll
+            for (int j = 0; j < kUnroll; ++j) __stcs(dst + i + j * stride, v[j]);
+        }
+    }
+    for (; i < nvec; i += stride) {
+        uint4 v;
+        if (MODE != B200PROBE_HBM_WRITE) v = __ldcs(src + i);
+        else {
+            uint64_t w = i * 4;
+            v = make_uint4(b200_pattern_word(w, a.seed), b200_pattern_word(w + 1, a.seed), b200_pattern_word(w + 2, a.seed),
+                           b200_pattern_word(w + 3, a.seed));
+        }
+        if (MODE == B200PROBE_HBM_READ) accum16(v, sum, x);
+        else __stcs(dst + i, v);
+    }
+    if (MODE == B200PROBE_HBM_READ) warp_publish(sum, x, a.partials);
+    tail_words(MODE, a, a.bytes & ~15ull);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Verification kernel: one streaming pass that (a) checksums the buffer (the data result compared
+// with the oracle) and (b) regenerates the closed-form pattern and counts words that differ
+// (the probe's own health verdict: a flipped bit anywhere in the swept range shows up here).
+// partials: [0] sum64, [1] xor32, [2] mismatching words, [3] index of the lowest mismatch.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(512) hbm_verify_kernel(const uint8_t* __restrict__ buf, uint64_t bytes, uint32_t seed,
+                                                         unsigned long long* partials) {
+    const uint64_t nvec = bytes >> 4;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    const uint4* __restrict__ src = reinterpret_cast<const uint4*>(buf);
+    unsigned long long sum = 0, bad = 0, first = ~0ull;
+    uint32_t x = 0;
+    auto check = [&](const uint4& v, uint64_t i) {
+        accum16(v, sum, x);
+        const uint64_t w = i * 4;
+        const uint32_t d = (v.x ^ b200_pattern_word(w, seed)) | (v.y ^ b200_pattern_word(w + 1, seed)) |
+                           (v.z ^ b200_pattern_word(w + 2, seed)) | (v.w ^ b200_pattern_word(w + 3, seed));
+        if (d) {
+            bad += (v.x != b200_pattern_word(w, seed)) + (v.y != b200_pattern_word(w + 1, seed)) + (v.z != b200_pattern_word(w + 2, seed)) +
+                   (v.w != b200_pattern_word(w + 3, seed));
+            first = min(first, (unsigned long long)w);
+        }
+    };
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    for (; i + 3 * stride < nvec; i += 4 * stride) {
+        uint4 v0 = __ldcs(src + i), v1 = __ldcs(src + i + stride), v2 = __ldcs(src + i + 2 * stride), v3 = __ldcs(src + i + 3 * stride);
+        check(v0, i); check(v1, i + stride); check(v2, i + 2 * stride); check(v3, i + 3 * stride);
+    }
+    for (; i < nvec; i += stride) check(__ldcs(src + i), i);
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        for (uint64_t off = bytes & ~15ull; off < bytes; off += 4) {
+            uint32_t w = *reinterpret_cast<const uint32_t*>(buf + off);
+            sum += w; x ^= w;
+            if (w != b200_pattern_word(off >> 2, seed)) { ++bad; first = min(first, (unsigned long long)(off >> 2)); }
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        sum += __shfl_xor_sync(0xffffffffu, sum, o);
+        x ^= __shfl_xor_sync(0xffffffffu, x, o);
+        bad += __shfl_xor_sync(0xffffffffu, bad, o);
+        first = min(first, (unsigned long long)__shfl_xor_sync(0xffffffffu, first, o));
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicAdd(partials, sum);
+        atomicXor(partials + 1, (unsigned long long)x);
+        if (bad) { atomicAdd(partials + 2, bad); atomicMin(partials + 3, first); }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Launch plumbing
+// ------------------------------------------------------------------------------------------------
+struct Tuning {
+    int variant, stage_bytes, stages, warps, ctas_per_sm;
+};
+
+Tuning resolve_tuning(const b200probe_hbm_cfg_t* c, int mode) {
+    Tuning t;
+    t.variant = c ? c->variant : B200PROBE_VARIANT_TMA;
+    t.stage_bytes = (c && c->stage_bytes) ? c->stage_bytes : 8192;
+    t.stages = (c && c->stages) ? c->stages : 4;
+    t.warps = (c && c->warps_per_cta) ? c->warps_per_cta : 4;
+    t.ctas_per_sm = (c && c->ctas_per_sm) ? c->ctas_per_sm : (t.variant == B200PROBE_VARIANT_TMA ? 1 : 4);
+    (void)mode;
+    return t;
+}
+
+int check_args(const void* p0, const void* p1, uint64_t bytes) {
+    if (bytes & 3) { b200::set_error("bytes=%llu is not a multiple of 4", (unsigned long long)bytes); return B200PROBE_EINVAL; }
+    if (((uintptr_t)p0 | (uintptr_t)p1) & 15) { b200::set_error("device pointers must be 16-byte aligned"); return B200PROBE_EINVAL; }
+    return 0;
+}
+
+template <int MODE>
+int launch_mode(int ordinal, RingArgs a, const b200probe_hbm_cfg_t* cfg, cudaStream_t stream) {
+    b200::DevProps props;
+    int rc = b200::device_props(ordinal, &props);
+    if (rc) return rc;
+    if (a.bytes == 0) return 0;
+    B200_CUDA_TRY(cudaSetDevice(ordinal));
+    Tuning t = resolve_tuning(cfg, MODE);
+    if (t.variant == B200PROBE_VARIANT_TMA) {
+        if (t.stages < 2 || t.stages > kMaxStages || t.warps < 1 || t.warps > kMaxWarps || t.stage_bytes < 512 || (t.stage_bytes & 511) ||
+            t.ctas_per_sm < 1) {
+            b200::set_error("bad TMA tuning: stage_bytes=%d stages=%d warps=%d ctas_per_sm=%d", t.stage_bytes, t.stages, t.warps, t.ctas_per_sm);
+            return B200PROBE_EINVAL;
+        }
+        size_t smem = (size_t)t.warps * t.stages * t.stage_bytes;
+        if (smem + 1024 > (size_t)props.smem_optin) {
+            b200::set_error("ring needs %zu B shared memory, device allows %d", smem, props.smem_optin);
+            return B200PROBE_EINVAL;
+        }
+        a.stage_bytes = (uint32_t)t.stage_bytes;
+        a.stages = (uint32_t)t.stages;
+        B200_CUDA_TRY(cudaFuncSetAttribute(hbm_ring_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int grid = props.sms * t.ctas_per_sm;
+        hbm_ring_kernel<MODE><<<grid, t.warps * 32, smem, stream>>>(a);
+    } else if (t.variant == B200PROBE_VARIANT_DIRECT) {
+        int grid = props.sms * t.ctas_per_sm;
+        hbm_direct_kernel<MODE><<<grid, 512, 0, stream>>>(a);
+    } else {
+        b200::set_error("unknown variant %d", t.variant);
+        return B200PROBE_EINVAL;
+    }
+    B200_CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+double median(std::vector<float> v) {
+    std::sort(v.begin(), v.end());
+    size_t n = v.size();
+    return n & 1 ? v[n / 2] : 0.5 * (v[n / 2 - 1] + v[n / 2]);
+}
+
+// Per-device resident arena: the probe runs periodically inside the plugin, so its buffers,
+// stream and events stay allocated between calls (cudaMalloc/cudaFree of 2 GiB costs more than
+// the sweep itself).  Released by b200probe_hbm_release / b200probe_shutdown.
+struct Arena {
+    pthread_mutex_t mu = PTHREAD_MUTEX_INITIALIZER;
+    uint8_t *src = nullptr, *dst = nullptr, *flush = nullptr;
+    uint64_t cap = 0, flush_cap = 0;
+    unsigned long long* partials = nullptr;     // 4 x u64
+    cudaStream_t stream = nullptr;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    uint64_t src_bytes = 0;                     // prefix of src currently holding pattern(src_seed)
+    uint32_t src_seed = 0;
+};
+Arena g_arena[B200PROBE_MAX_DEVICES];
+
+struct ArenaLock {
+    Arena& a;
+    explicit ArenaLock(Arena& x) : a(x) { pthread_mutex_lock(&a.mu); }
+    ~ArenaLock() { pthread_mutex_unlock(&a.mu); }
+};
+
+void arena_free(Arena& a) {
+    if (a.src) cudaFree(a.src);
+    if (a.dst) cudaFree(a.dst);
+    if (a.flush) cudaFree(a.flush);
+    if (a.partials) cudaFree(a.partials);
+    if (a.e0) cudaEventDestroy(a.e0);
+    if (a.e1) cudaEventDestroy(a.e1);
+    if (a.stream) cudaStreamDestroy(a.stream);
+    a.src = a.dst = a.flush = nullptr;
+    a.partials = nullptr; a.e0 = a.e1 = nullptr; a.stream = nullptr;
+    a.cap = a.flush_cap = a.src_bytes = 0;
+}
+
+int arena_reserve(Arena& a, uint64_t bytes, uint64_t flush_bytes) {
+    if (!a.stream) {
+        B200_CUDA_TRY(cudaStreamCreateWithFlags(&a.stream, cudaStreamNonBlocking));
+        B200_CUDA_TRY(cudaEventCreate(&a.e0));
+        B200_CUDA_TRY(cudaEventCreate(&a.e1));
+        B200_CUDA_TRY(cudaMalloc(&a.partials, 32));
+    }
+    if (bytes > a.cap) {
+        if (a.src) cudaFree(a.src);
+        if (a.dst) cudaFree(a.dst);
+        a.src = a.dst = nullptr; a.cap = 0; a.src_bytes = 0;
+        B200_CUDA_TRY(cudaMalloc(&a.src, bytes));
+        B200_CUDA_TRY(cudaMalloc(&a.dst, bytes));
+        a.cap = bytes;
+    }
+    if (flush_bytes > a.flush_cap) {
+        if (a.flush) cudaFree(a.flush);
+        a.flush = nullptr; a.flush_cap = 0;
+        B200_CUDA_TRY(cudaMalloc(&a.flush, flush_bytes));
+        a.flush_cap = flush_bytes;
+    }
+    return 0;
+}
+
+struct VerifyOut { uint64_t sum; uint32_t x; uint64_t bad, first; };
+
+int verify_pass(int ordinal, const uint8_t* buf, uint64_t bytes, uint32_t seed, Arena& a, int sms, VerifyOut* v) {
+    static const unsigned long long init[4] = {0, 0, 0, ~0ull};
+    B200_CUDA_TRY(cudaMemcpyAsync(a.partials, init, 32, cudaMemcpyHostToDevice, a.stream));
+    if (bytes) {
+        hbm_verify_kernel<<<sms * 4, 512, 0, a.stream>>>(buf, bytes, seed, a.partials);
+        B200_CUDA_TRY(cudaGetLastError());
+    }
+    unsigned long long h[4];
+    B200_CUDA_TRY(cudaMemcpyAsync(h, a.partials, 32, cudaMemcpyDeviceToHost, a.stream));
+    B200_CUDA_TRY(cudaStreamSynchronize(a.stream));
+    v->sum = h[0]; v->x = (uint32_t)h[1]; v->bad = h[2]; v->first = h[3];
+    (void)ordinal;
+    return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int b200probe_hbm_fill(int ordinal, void* dst, uint64_t bytes, uint32_t seed, const b200probe_hbm_cfg_t* cfg, void* stream) {
+    int rc = check_args(dst, nullptr, bytes);
+    if (rc) return rc;
+    RingArgs a{nullptr, (uint8_t*)dst, bytes, seed, 0, 0, nullptr};
+    return launch_mode<B200PROBE_HBM_WRITE>(ordinal, a, cfg, (cudaStream_t)stream);
+}
+
+int b200probe_hbm_copy(int ordinal, const void* src, void* dst, uint64_t bytes, const b200probe_hbm_cfg_t* cfg, void* stream) {
+    int rc = check_args(src, dst, bytes);
+    if (rc) return rc;
+    RingArgs a{(const uint8_t*)src, (uint8_t*)dst, bytes, 0, 0, 0, nullptr};
+    return launch_mode<B200PROBE_HBM_COPY>(ordinal, a, cfg, (cudaStream_t)stream);
+}
+
+int b200probe_hbm_read(int ordinal, const void* src, uint64_t bytes, uint64_t* partials, const b200probe_hbm_cfg_t* cfg, void* stream) {
+    int rc = check_args(src, partials, bytes);
+    if (rc) return rc;
+    if (!partials) return B200PROBE_EINVAL;
+    RingArgs a{(const uint8_t*)src, nullptr, bytes, 0, 0, 0, (unsigned long long*)partials};
+    return launch_mode<B200PROBE_HBM_READ>(ordinal, a, cfg, (cudaStream_t)stream);
+}
+
+int b200probe_hbm_copy_host(int ordinal, const void* src_host, void* dst_host, uint64_t bytes, uint64_t* sum64, uint32_t* xor32) {
+    if ((bytes & 3) || (bytes && (!src_host || !dst_host))) { b200::set_error("copy_host: bad arguments"); return B200PROBE_EINVAL; }
+    b200::DevProps props;
+    int rc = b200::device_props(ordinal, &props);
+    if (rc) return rc;
+    B200_CUDA_TRY(cudaSetDevice(ordinal));
+    Arena& a = g_arena[ordinal];
+    ArenaLock lock(a);
+    rc = arena_reserve(a, std::max<uint64_t>(bytes, 16), 0);
+    if (rc) return rc;
+    a.src_bytes = 0;   // src no longer holds the pattern
+    B200_CUDA_TRY(cudaMemcpyAsync(a.src, src_host, bytes, cudaMemcpyHostToDevice, a.stream));
+    rc = b200probe_hbm_copy(ordinal, a.src, a.dst, bytes, nullptr, a.stream);
+    if (rc) return rc;
+    VerifyOut v;
+    rc = verify_pass(ordinal, a.dst, bytes, 0, a, props.sms, &v);   // checksum only; mismatch count is meaningless for user data
+    if (rc) return rc;
+    B200_CUDA_TRY(cudaMemcpyAsync(dst_host, a.dst, bytes, cudaMemcpyDeviceToHost, a.stream));
+    B200_CUDA_TRY(cudaStreamSynchronize(a.stream));
+    if (sum64) *sum64 = v.sum;
+    if (xor32) *xor32 = v.x;
+    return 0;
+}
+
+int b200probe_hbm_release(int ordinal) {
+    if (ordinal < 0 || ordinal >= B200PROBE_MAX_DEVICES) return B200PROBE_ERANGE;
+    Arena& a = g_arena[ordinal];
+    ArenaLock lock(a);
+    if (a.stream) { cudaSetDevice(ordinal); arena_free(a); }
+    return 0;
+}
+
+int b200probe_hbm_sweep(int idx, const b200probe_hbm_cfg_t* cfg_in, b200probe_hbm_result_t* out, int cap, int* n_out) {
+    if (!out || !n_out || cap <= 0) return B200PROBE_EINVAL;
+    int ordinal = -1;
+    int rc = b200::cuda_ordinal_of(idx, &ordinal);
+    if (rc) return rc;
+    b200::DevProps props;
+    rc = b200::device_props(ordinal, &props);
+    if (rc) return rc;
+
+    b200probe_hbm_cfg_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    if (cfg_in) cfg = *cfg_in;
+    if (!cfg.min_bytes) cfg.min_bytes = 1ull << 20;
+    if (!cfg.max_bytes) cfg.max_bytes = 1ull << 30;
+    if (!cfg.modes) cfg.modes = B200PROBE_HBM_READ | B200PROBE_HBM_WRITE | B200PROBE_HBM_COPY;
+    if (!cfg.warmup && !cfg.reps) { cfg.warmup = 3; cfg.reps = 20; }
+    if (cfg.reps < 1) cfg.reps = 1;
+    if (!cfg.seed) cfg.seed = 0xB200u;
+    if (cfg.min_bytes > cfg.max_bytes || (cfg.min_bytes & (cfg.min_bytes - 1)) || (cfg.max_bytes & (cfg.max_bytes - 1)) || cfg.min_bytes < 16) {
+        b200::set_error("sweep sizes must be powers of two, min<=max, min>=16");
+        return B200PROBE_EINVAL;
+    }
+
+    B200_CUDA_TRY(cudaSetDevice(ordinal));
+    Arena& a = g_arena[ordinal];
+    ArenaLock lock(a);
+    const size_t flush_bytes = cfg.flush_l2 ? (size_t)props.l2_bytes * 2 : 0;
+    rc = arena_reserve(a, cfg.max_bytes, flush_bytes);
+    if (rc) return rc;
+
+    // source pattern (also the expected content of every mode's result); kept across calls
+    if (a.src_bytes < cfg.max_bytes || a.src_seed != cfg.seed) {
+        rc = b200probe_hbm_fill(ordinal, a.src, cfg.max_bytes, cfg.seed, &cfg, a.stream);
+        if (rc) return rc;
+        a.src_bytes = cfg.max_bytes;
+        a.src_seed = cfg.seed;
+    }
+
+    int n = 0;
+    const int mode_list[3] = {B200PROBE_HBM_READ, B200PROBE_HBM_WRITE, B200PROBE_HBM_COPY};
+    std::vector<float> ms((size_t)cfg.reps);
+    for (uint64_t bytes = cfg.min_bytes; bytes <= cfg.max_bytes; bytes <<= 1) {
+        for (int mi = 0; mi < 3; ++mi) {
+            const int mode = mode_list[mi];
+            if (!(cfg.modes & mode)) continue;
+            if (n >= cap) { b200::set_error("result buffer too small (cap=%d)", cap); return B200PROBE_ERANGE; }
+            b200probe_hbm_result_t& r = out[n];
+            memset(&r, 0, sizeof(r));
+            r.bytes = bytes; r.mode = mode; r.variant = cfg.variant; r.verified = -1;
+            const uint64_t footprint = mode == B200PROBE_HBM_COPY ? 2 * bytes : bytes;
+            r.cache_resident = footprint <= (uint64_t)props.l2_bytes;
+            if (mode != B200PROBE_HBM_READ && cfg.verify) B200_CUDA_TRY(cudaMemsetAsync(a.dst, 0, bytes, a.stream));
+            B200_CUDA_TRY(cudaMemsetAsync(a.partials, 0, 32, a.stream));
+            for (int it = -cfg.warmup; it < cfg.reps; ++it) {
+                if (cfg.flush_l2) B200_CUDA_TRY(cudaMemsetAsync(a.flush, it & 0xff, flush_bytes, a.stream));
+                if (it >= 0) B200_CUDA_TRY(cudaEventRecord(a.e0, a.stream));
+                if (mode == B200PROBE_HBM_READ) rc = b200probe_hbm_read(ordinal, a.src, bytes, (uint64_t*)a.partials, &cfg, a.stream);
+                else if (mode == B200PROBE_HBM_WRITE) rc = b200probe_hbm_fill(ordinal, a.dst, bytes, cfg.seed, &cfg, a.stream);
+                else rc = b200probe_hbm_copy(ordinal, a.src, a.dst, bytes, &cfg, a.stream);
+                if (rc) return rc;
+                if (it >= 0) {
+                    B200_CUDA_TRY(cudaEventRecord(a.e1, a.stream));
+                    B200_CUDA_TRY(cudaEventSynchronize(a.e1));
+                    B200_CUDA_TRY(cudaEventElapsedTime(&ms[it], a.e0, a.e1));
+                }
+            }
+            r.ms_median = median(ms);
+            r.ms_best = *std::min_element(ms.begin(), ms.end());
+            const double alg = (double)(mode == B200PROBE_HBM_COPY ? 2 * bytes : bytes);
+            r.gbs_median = alg / (r.ms_median * 1e-3) / 1e9;
+            r.gbs_best = alg / (r.ms_best * 1e-3) / 1e9;
+            if (cfg.verify) {
+                // one clean pass over the buffer the mode produced (write/copy) or consumed (read):
+                // checksum = data result, mismatch count vs the regenerated pattern = verdict
+                VerifyOut v;
+                rc = verify_pass(ordinal, mode == B200PROBE_HBM_READ ? a.src : a.dst, bytes, cfg.seed, a, props.sms, &v);
+                if (rc) return rc;
+                r.sum64 = v.sum; r.xor32 = v.x;
+                r.verified = v.bad == 0 ? 1 : 0;
+                if (v.bad) {
+                    b200::set_error("HBM sweep: %llu words differ from the pattern at %llu bytes mode %d (first bad word %llu)",
+                                    (unsigned long long)v.bad, (unsigned long long)bytes, mode, (unsigned long long)v.first);
+                    *n_out = n + 1;
+                    return B200PROBE_EMISMATCH;
+                }
+            } else {
+                B200_CUDA_TRY(cudaStreamSynchronize(a.stream));
+            }
+            ++n;
+        }
+    }
+    *n_out = n;
+    return 0;
+}
+
+}  // extern "C"

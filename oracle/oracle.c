@@ -1,0 +1,162 @@
+/*
+ * oracle.c — CPU restatement of the probe path's DATA results.  TEST INFRASTRUCTURE ONLY.
+ *
+ * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
+ * load this.  The product (k3s-nvidia_b200/) never imports, links or executes anything here.
+ *
+ * PARITY UNPINNED: the reference repository (/root/reference, six non-code files) contains no
+ * implementation, no tests and no golden vectors for this path, and the component it installs
+ * (NVIDIA k8s-device-plugin Helm chart, /root/reference/README.md:109,116) is un-pinned and
+ * un-vendored.  What this file restates instead:
+ *   - the synthetic data contract of SURVEY.md §8d  (u32 counter pattern x[i] = i*2654435761 ^ seed,
+ *     seed 0xB200; checksum = sum mod 2^64 and xor of the u32 words),
+ *   - the NVLink chunk-seed rule and the GEMM operand generator + fp64 contraction,
+ * written independently of k3s-nvidia_b200/csrc (no shared header), so a transcription error in
+ * either shows up as a parity failure.  The passive-health twin is in passive_health_oracle.c.
+ */
+#define _GNU_SOURCE
+#include <math.h>
+#include <pthread.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+#include <time.h>
+
+/* ---- HBM sweep data ------------------------------------------------ */
+static inline uint32_t pat(uint64_t i, uint32_t seed) {
+    uint32_t lo = (uint32_t)(i & 0xffffffffu), hi = (uint32_t)(i >> 32);
+    return (uint32_t)(lo * 2654435761u) ^ seed ^ hi;
+}
+
+uint32_t oracle_pattern_word(uint64_t i, uint32_t seed) { return pat(i, seed); }
+
+void oracle_pattern_fill(uint32_t* dst, uint64_t first_word, uint64_t words, uint32_t seed) {
+    for (uint64_t i = 0; i < words; ++i) dst[i] = pat(first_word + i, seed);
+}
+
+void oracle_checksum(const uint32_t* buf, uint64_t words, uint64_t* sum64, uint32_t* xor32) {
+    uint64_t s = 0;
+    uint32_t x = 0;
+    for (uint64_t i = 0; i < words; ++i) { s += buf[i]; x ^= buf[i]; }
+    *sum64 = s;
+    *xor32 = x;
+}
+
+/* expected checksum of pattern words [0, words) without materialising the buffer */
+void oracle_pattern_checksum(uint64_t words, uint32_t seed, uint64_t* sum64, uint32_t* xor32) {
+    uint64_t s = 0;
+    uint32_t x = 0;
+    for (uint64_t i = 0; i < words; ++i) { uint32_t w = pat(i, seed); s += w; x ^= w; }
+    *sum64 = s;
+    *xor32 = x;
+}
+
+void oracle_copy(void* dst, const void* src, uint64_t bytes) { memmove(dst, src, bytes); }
+
+/* ---- multi-threaded host sweep: the "port" CPU baseline --------------------------------------
+ * mode 1 read (checksum), 2 write (pattern fill), 4 copy; each thread owns a contiguous slice. */
+typedef struct {
+    uint32_t *src, *dst;
+    uint64_t first, words;
+    uint32_t seed;
+    int mode, reps;
+    uint64_t sum;
+    uint32_t x;
+} slice_t;
+
+static void* slice_run(void* p) {
+    slice_t* s = (slice_t*)p;
+    for (int r = 0; r < s->reps; ++r) {
+        if (s->mode == 1) {
+            uint64_t a; uint32_t b;
+            oracle_checksum(s->src + s->first, s->words, &a, &b);
+            s->sum = a; s->x = b;
+        } else if (s->mode == 2) {
+            oracle_pattern_fill(s->dst + s->first, s->first, s->words, s->seed);
+        } else {
+            memcpy(s->dst + s->first, s->src + s->first, s->words * 4);
+        }
+    }
+    return NULL;
+}
+
+static double now_s(void) {
+    struct timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return ts.tv_sec + ts.tv_nsec * 1e-9;
+}
+
+/* Runs `reps` passes of `mode` over `bytes` of host memory with `threads` threads.
+ * Returns seconds for the timed passes (buffers are allocated + first-touched outside the timing);
+ * the data result of the last pass is returned through sum64/xor32 (read: checksum of src;
+ * write/copy: checksum of dst). */
+double oracle_host_sweep(uint64_t bytes, int threads, int mode, int reps, uint32_t seed, uint64_t* sum64, uint32_t* xor32) {
+    uint64_t words = bytes / 4;
+    if (threads < 1) threads = 1;
+    uint32_t* src = (uint32_t*)aligned_alloc(4096, (bytes + 4095) & ~4095ull);
+    uint32_t* dst = (uint32_t*)aligned_alloc(4096, (bytes + 4095) & ~4095ull);
+    if (!src || !dst) { free(src); free(dst); return -1.0; }
+    slice_t* sl = (slice_t*)calloc((size_t)threads, sizeof(slice_t));
+    pthread_t* th = (pthread_t*)calloc((size_t)threads, sizeof(pthread_t));
+    uint64_t per = (words + threads - 1) / threads;
+    /* first touch in parallel with the same slicing (NUMA placement), untimed */
+    for (int t = 0; t < threads; ++t) {
+        uint64_t f = per * t, w = f >= words ? 0 : (words - f < per ? words - f : per);
+        sl[t] = (slice_t){src, src, f, w, seed, 2, 1, 0, 0};
+        pthread_create(&th[t], NULL, slice_run, &sl[t]);
+    }
+    for (int t = 0; t < threads; ++t) pthread_join(th[t], NULL);
+    for (int t = 0; t < threads; ++t) { sl[t].dst = dst; sl[t].mode = 4; pthread_create(&th[t], NULL, slice_run, &sl[t]); }
+    for (int t = 0; t < threads; ++t) pthread_join(th[t], NULL);
+    if (mode != 4) memset(dst, 0, bytes);
+    double t0 = now_s();
+    for (int t = 0; t < threads; ++t) { sl[t].mode = mode; sl[t].reps = reps; pthread_create(&th[t], NULL, slice_run, &sl[t]); }
+    for (int t = 0; t < threads; ++t) pthread_join(th[t], NULL);
+    double dt = now_s() - t0;
+    oracle_checksum(mode == 1 ? src : dst, words, sum64, xor32);
+    free(sl); free(th); free(src); free(dst);
+    return dt;
+}
+
+/* ---- NVLink all-to-all data ------------------------------------------ */
+static inline uint32_t mix32(uint32_t x) {
+    x ^= x >> 16; x *= 0x7feb352du; x ^= x >> 15; x *= 0x846ca68bu; x ^= x >> 16;
+    return x;
+}
+/* chunk sent by rank src to rank dst carries pattern words under this seed */
+uint32_t oracle_a2a_chunk_seed(uint32_t seed, int src, int dst) { return seed ^ mix32((uint32_t)(src * 251 + dst * 7 + 1)); }
+
+/* ---- GEMM probe data (SURVEY.md §8d "GEMM probe") --------------------------------------------- */
+/* Operand element e of matrix `which` (0 = A [m][k], 1 = B [n][k]) is k/128 with integer
+ * k in [-128,127]: exactly representable in bf16, products and K<=65536-term sums exact in fp32
+ * and fp64, so C is a pure function of the inputs up to ONE final rounding to bf16. */
+double oracle_gemm_elem(uint64_t e, uint32_t seed, int which) {
+    uint32_t lo = (uint32_t)(e & 0xffffffffu), hi = (uint32_t)(e >> 32);
+    uint32_t h = mix32((lo * 0x9E3779B1u) ^ mix32(seed + 0x51ED27u * (uint32_t)(which + 1)) ^ hi);
+    int k = (int)(h & 0xFF) - 128;
+    return (double)k / 128.0;
+}
+
+uint16_t oracle_gemm_elem_bits(uint64_t e, uint32_t seed, int which) {
+    float f = (float)oracle_gemm_elem(e, seed, which);
+    uint32_t u;
+    memcpy(&u, &f, 4);
+    return (uint16_t)(u >> 16);
+}
+
+/* C[row][col] = sum_k A[row][k] * B[col][k], in fp64 */
+double oracle_gemm_dot(int kdim, uint32_t seed, int row, int col) {
+    double acc = 0.0;
+    for (int k = 0; k < kdim; ++k)
+        acc += oracle_gemm_elem((uint64_t)row * kdim + k, seed, 0) * oracle_gemm_elem((uint64_t)col * kdim + k, seed, 1);
+    return acc;
+}
+
+/* round-to-nearest-even fp32 -> bf16 bits (the conversion the epilogue applies) */
+uint16_t oracle_bf16_rne(float f) {
+    uint32_t u;
+    memcpy(&u, &f, 4);
+    if ((u & 0x7fffffffu) > 0x7f800000u) return (uint16_t)((u >> 16) | 0x40);   /* NaN */
+    uint32_t r = 0x7fffu + ((u >> 16) & 1u);
+    return (uint16_t)((u + r) >> 16);
+}

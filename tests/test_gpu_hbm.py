@@ -1,0 +1,121 @@
+"""GPU parity: the sm_100a HBM kernels (through the C ABI) against the CPU oracle.  Bit-exact."""
+import numpy as np
+import pytest
+
+import _oracle
+
+pytestmark = pytest.mark.gpu
+
+SEED = 0xB200
+TUNINGS = [
+    dict(variant=0),                                                   # TMA ring, defaults
+    dict(variant=0, stage_bytes=4096, stages=2, warps_per_cta=1),      # smallest ring
+    dict(variant=0, stage_bytes=16384, stages=3, warps_per_cta=4),
+    dict(variant=0, stage_bytes=8192, stages=8, warps_per_cta=2, ctas_per_sm=1),
+    dict(variant=1),                                                   # direct LDG/STG
+]
+# ragged, tiny, empty, below/above one ring chunk, non-16-multiples (word tail)
+SIZES = [0, 4, 12, 16, 20, 4096, 4100, 8192 + 8, 65536 - 4, 1 << 20, (1 << 20) + 4, 3 * (1 << 20) + 36, 37 * 8192 * 4 + 16]
+
+
+@pytest.fixture(scope="module")
+def env():
+    import torch
+
+    from k3s_nvidia_b200.probe import Probe
+
+    assert torch.cuda.is_available()
+    return torch, Probe(), _oracle.load()
+
+
+def _dev_checksum(torch, p, t, nbytes, **tuning):
+    part = torch.zeros(2, dtype=torch.int64, device="cuda:0")
+    p.hbm_read(0, t.data_ptr(), nbytes, part.data_ptr(), torch.cuda.current_stream().cuda_stream, **tuning)
+    torch.cuda.synchronize()
+    return part[0].item() & 0xFFFFFFFFFFFFFFFF, part[1].item() & 0xFFFFFFFF
+
+
+@pytest.mark.parametrize("tuning", TUNINGS, ids=lambda t: "-".join(f"{k}{v}" for k, v in t.items()))
+@pytest.mark.parametrize("nbytes", SIZES)
+def test_fill_copy_read_match_oracle(env, tuning, nbytes):
+    torch, p, o = env
+    st = torch.cuda.current_stream().cuda_stream
+    pad = 64
+    src = torch.full((nbytes + pad,), 0xAA, dtype=torch.uint8, device="cuda:0")
+    dst = torch.full((nbytes + pad,), 0x55, dtype=torch.uint8, device="cuda:0")
+    p.hbm_fill(0, src.data_ptr(), nbytes, SEED, st, **tuning)
+    p.hbm_copy(0, src.data_ptr(), dst.data_ptr(), nbytes, st, **tuning)
+    torch.cuda.synchronize()
+    want = _oracle.pattern(o, 0, nbytes // 4, SEED)
+    got_src = src.cpu().numpy()
+    got_dst = dst.cpu().numpy()
+    assert np.array_equal(got_src[:nbytes].view(np.uint32), want), "fill differs from oracle"
+    assert np.array_equal(got_dst[:nbytes].view(np.uint32), want), "copy differs from oracle"
+    assert (got_src[nbytes:] == 0xAA).all() and (got_dst[nbytes:] == 0x55).all(), "wrote past the end"
+    assert _dev_checksum(torch, p, dst, nbytes, **tuning) == _oracle.pattern_checksum(o, nbytes // 4, SEED)
+
+
+def test_read_checksum_of_arbitrary_data(env):
+    torch, p, o = env
+    g = torch.Generator(device="cpu").manual_seed(7)
+    host = torch.randint(0, 256, (5 * (1 << 20) + 52,), dtype=torch.uint8, generator=g)
+    dev = host.cuda()
+    for tuning in TUNINGS:
+        assert _dev_checksum(torch, p, dev, host.numel(), **tuning) == _oracle.checksum(o, host.numpy())
+
+
+def test_copy_host_roundtrip(env):
+    torch, p, o = env
+    rng = np.random.default_rng(3)
+    src = rng.integers(0, 2**32, size=(1 << 22) + 3, dtype=np.uint32)
+    dst = np.zeros_like(src)
+    s, x = p.hbm_copy_host(0, src, dst)
+    assert np.array_equal(src, dst)
+    assert (s, x) == _oracle.checksum(o, src)
+
+
+def test_full_size_properties(env):
+    """BASELINE config 2 at its largest size (1 GiB): closed-form checksum of the pattern,
+    copy == source (checksum of checksums), idempotence of a second copy."""
+    torch, p, o = env
+    nbytes = 1 << 30
+    st = torch.cuda.current_stream().cuda_stream
+    src = torch.empty(nbytes, dtype=torch.uint8, device="cuda:0")
+    dst = torch.zeros(nbytes, dtype=torch.uint8, device="cuda:0")
+    p.hbm_fill(0, src.data_ptr(), nbytes, SEED, st)
+    want = _oracle.pattern_checksum(o, nbytes // 4, SEED)
+    assert _dev_checksum(torch, p, src, nbytes) == want
+    assert _dev_checksum(torch, p, src, nbytes, variant=1) == want
+    p.hbm_copy(0, src.data_ptr(), dst.data_ptr(), nbytes, st)
+    assert _dev_checksum(torch, p, dst, nbytes) == want
+    p.hbm_copy(0, dst.data_ptr(), src.data_ptr(), nbytes, st, variant=1)
+    assert _dev_checksum(torch, p, src, nbytes) == want
+    # spot-check 1 MiB windows byte-for-byte against the oracle
+    for off in (0, (1 << 29) - (1 << 19), nbytes - (1 << 20)):
+        got = dst[off: off + (1 << 20)].cpu().numpy().view(np.uint32)
+        assert np.array_equal(got, _oracle.pattern(o, off // 4, (1 << 20) // 4, SEED))
+
+
+def test_sweep_default_config_verified(env):
+    torch, p, o = env
+    pts = p.hbm_sweep(0, min_bytes=1 << 20, max_bytes=1 << 28, warmup=1, reps=3, verify=1)
+    assert len(pts) == 9 * 3
+    for pt in pts:
+        assert pt.verified == 1
+        assert (pt.sum64, pt.xor32) == _oracle.pattern_checksum(o, pt.bytes // 4, SEED)
+        assert pt.gbs_median > 0
+
+
+def test_bad_arguments_fail_loudly(env):
+    torch, p, o = env
+    from k3s_nvidia_b200.probe import ProbeError
+
+    t = torch.zeros(1024, dtype=torch.uint8, device="cuda:0")
+    with pytest.raises(ProbeError):
+        p.hbm_fill(0, t.data_ptr(), 6, SEED)            # not a multiple of 4
+    with pytest.raises(ProbeError):
+        p.hbm_fill(0, t.data_ptr() + 4, 16, SEED)       # misaligned
+    with pytest.raises(ProbeError):
+        p.hbm_fill(0, t.data_ptr(), 16, SEED, variant=0, stages=1)
+    with pytest.raises(ProbeError):
+        p.hbm_fill(99, t.data_ptr(), 16, SEED)
