@@ -198,6 +198,9 @@ typedef struct b200probe_a2a_result {
 int b200probe_nvlink_a2a(const int* cuda_ordinals, int g, const b200probe_a2a_cfg_t* cfg,
                          double* pair_gbs, b200probe_a2a_result_t* out);
 
+/* Enable peer access between every ordered pair of the listed devices (idempotent). */
+int b200probe_enable_peer_access(const int* cuda_ordinals, int g);
+
 /* One process per GPU (bench under torchrun): each rank allocates its receive window, exports a
  * 64-byte IPC handle, the host exchanges handles (any transport), imports the peers' windows and
  * pushes its chunks into them.  window layout on every rank: [world][S] bytes, slot r = data

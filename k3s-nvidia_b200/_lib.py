@@ -169,6 +169,7 @@ SIGNATURES = {
     "b200probe_hbm_read": (C.c_int, [C.c_int, _vp, C.c_uint64, _vp, _P(HbmCfg), _vp]),
     "b200probe_hbm_copy_host": (C.c_int, [C.c_int, _vp, _vp, C.c_uint64, _P(C.c_uint64), _P(C.c_uint32)]),
     "b200probe_nvlink_a2a": (C.c_int, [_P(C.c_int), C.c_int, _P(A2aCfg), _P(C.c_double), _P(A2aResult)]),
+    "b200probe_enable_peer_access": (C.c_int, [_P(C.c_int), C.c_int]),
     "b200probe_a2a_window_create": (C.c_int, [C.c_int, C.c_int, C.c_uint64, _P(_vp), C.c_char_p]),
     "b200probe_a2a_window_import": (C.c_int, [C.c_int, C.c_char_p, _P(_vp)]),
     "b200probe_a2a_window_release": (C.c_int, [C.c_int, _vp, C.c_int]),

@@ -351,14 +351,20 @@ struct Tuning {
     int variant, stage_bytes, stages, warps, ctas_per_sm;
 };
 
+// Defaults per mode from the 1 GiB tuning sweep on B200 (profiles/hbm_tune_r01_1GiB.txt):
+//   copy  8 KiB x 4 stages x 2 warps, 1 CTA/SM  -> 6515 GB/s (torch copy_ 6400)
+//   read  8 KiB x 3 stages x 4 warps            -> 6890 GB/s
+//   write 8 KiB x 6 stages x 4 warps            -> 7024 GB/s
+// More bytes in flight than ~64-190 KB/SM makes copy slower (DRAM read/write turnarounds), not faster.
 Tuning resolve_tuning(const b200probe_hbm_cfg_t* c, int mode) {
     Tuning t;
     t.variant = c ? c->variant : B200PROBE_VARIANT_TMA;
+    const int d_stages = mode == B200PROBE_HBM_COPY ? 4 : mode == B200PROBE_HBM_READ ? 3 : 6;
+    const int d_warps = mode == B200PROBE_HBM_COPY ? 2 : 4;
     t.stage_bytes = (c && c->stage_bytes) ? c->stage_bytes : 8192;
-    t.stages = (c && c->stages) ? c->stages : 4;
-    t.warps = (c && c->warps_per_cta) ? c->warps_per_cta : 4;
-    t.ctas_per_sm = (c && c->ctas_per_sm) ? c->ctas_per_sm : (t.variant == B200PROBE_VARIANT_TMA ? 1 : 4);
-    (void)mode;
+    t.stages = (c && c->stages) ? c->stages : d_stages;
+    t.warps = (c && c->warps_per_cta) ? c->warps_per_cta : d_warps;
+    t.ctas_per_sm = (c && c->ctas_per_sm) ? c->ctas_per_sm : (t.variant == B200PROBE_VARIANT_TMA ? 1 : (mode == B200PROBE_HBM_READ ? 3 : 8));
     return t;
 }
 

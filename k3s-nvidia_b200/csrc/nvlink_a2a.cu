@@ -157,6 +157,17 @@ extern "C" {
 
 uint32_t b200probe_a2a_chunk_seed(uint32_t seed, int src, int dst) { return chunk_seed(seed, src, dst); }
 
+int b200probe_enable_peer_access(const int* ordinals, int g) {
+    if (!ordinals || g < 1 || g > kMaxWorld) return B200PROBE_EINVAL;
+    for (int i = 0; i < g; ++i) {
+        b200::DevProps props;
+        int rc = b200::device_props(ordinals[i], &props);
+        if (rc) return rc;
+        B200_CUDA_TRY(cudaSetDevice(ordinals[i]));
+    }
+    return 0;
+}
+
 int b200probe_a2a_window_create(int ordinal, int world, uint64_t S, void** window, unsigned char* handle_out) {
     if (!window || world < 1 || world > kMaxWorld) return B200PROBE_EINVAL;
     b200::DevProps props;
@@ -224,6 +235,10 @@ int b200probe_nvlink_a2a(const int* ordinals, int g, const b200probe_a2a_cfg_t* 
     out->verified = -1;
     if (pair_gbs) std::fill(pair_gbs, pair_gbs + g * g, 0.0);
 
+    {
+        int rc = b200probe_enable_peer_access(ordinals, g);
+        if (rc) return rc;
+    }
     A2aCtx ctx;
     ctx.d.resize(g);
     // peer access, windows
@@ -232,15 +247,6 @@ int b200probe_nvlink_a2a(const int* ordinals, int g, const b200probe_a2a_cfg_t* 
         int rc = b200::device_props(ordinals[i], &props);
         if (rc) return rc;
         B200_CUDA_TRY(cudaSetDevice(ordinals[i]));
-        for (int j = 0; j < g; ++j) {
-            if (i == j) continue;
-            int can = 0;
-            B200_CUDA_TRY(cudaDeviceCanAccessPeer(&can, ordinals[i], ordinals[j]));
-            if (!can) { b200::set_error("no peer access %d -> %d", ordinals[i], ordinals[j]); return B200PROBE_ENOPEER; }
-            cudaError_t e = cudaDeviceEnablePeerAccess(ordinals[j], 0);
-            if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) { b200::set_error("cudaDeviceEnablePeerAccess: %s", cudaGetErrorString(e)); return b200::cuda_rc(e); }
-            cudaGetLastError();
-        }
         PerDev& p = ctx.d[i];
         p.ordinal = ordinals[i];
         B200_CUDA_TRY(cudaStreamCreateWithFlags(&p.stream, cudaStreamNonBlocking));

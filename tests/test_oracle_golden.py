@@ -1,0 +1,79 @@
+"""The CPU oracle pinned against the committed golden vectors (tests/golden/golden.json, generated
+by tests/golden/make_golden.py from an independent pure-Python restatement).  The reference holds
+no vectors for this path ("parity unpinned") — this is the strongest pin available."""
+import ctypes as C
+import json
+import os
+
+import numpy as np
+import pytest
+
+import _oracle
+
+G = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "golden.json")))
+
+
+@pytest.fixture(scope="module")
+def o():
+    return _oracle.load()
+
+
+def test_pattern_words(o):
+    for i, seed, want in G["pattern"]:
+        assert o.oracle_pattern_word(i, seed) == want
+
+
+def test_pattern_fill_matches_words(o):
+    a = _oracle.pattern(o, 2**32 - 3, 8, 0xB200)
+    assert [int(v) for v in a] == [o.oracle_pattern_word(2**32 - 3 + j, 0xB200) for j in range(8)]
+
+
+def test_checksums(o):
+    for words, seed, s, x in G["checksum"]:
+        assert _oracle.pattern_checksum(o, words, seed) == (s, x)
+        if words <= 1 << 20:
+            assert _oracle.checksum(o, _oracle.pattern(o, 0, words, seed)) == (s, x)
+
+
+def test_checksum_is_order_independent_and_additive(o):
+    a = _oracle.pattern(o, 0, 4096, 7)
+    rng = np.random.default_rng(0)
+    b = a.copy()
+    rng.shuffle(b)
+    assert _oracle.checksum(o, a) == _oracle.checksum(o, b)
+    s1, x1 = _oracle.checksum(o, np.ascontiguousarray(a[:1000]))
+    s2, x2 = _oracle.checksum(o, np.ascontiguousarray(a[1000:]))
+    s, x = _oracle.checksum(o, a)
+    assert ((s1 + s2) & (2**64 - 1), x1 ^ x2) == (s, x)
+
+
+def test_a2a_chunk_seeds(o):
+    for seed, src, dst, want in G["a2a_seed"]:
+        assert o.oracle_a2a_chunk_seed(seed, src, dst) == want
+    seeds = {o.oracle_a2a_chunk_seed(0xB200, s, d) for s in range(8) for d in range(8)}
+    assert len(seeds) == 64          # every (src,dst) chunk is distinguishable
+
+
+def test_gemm_elements_and_dots(o):
+    for e, seed, which, k, bits in G["gemm_elem"]:
+        assert o.oracle_gemm_elem(e, seed, which) == k / 128.0
+        assert o.oracle_gemm_elem_bits(e, seed, which) == bits
+    for kdim, row, col, acc, val, bits in G["gemm_dot"]:
+        got = o.oracle_gemm_dot(kdim, 0xB200, row, col)
+        assert got == val                                  # exact in fp64
+        assert got * 16384 == acc
+        assert o.oracle_bf16_rne(got) == bits
+
+
+def test_bf16_rne(o):
+    for f, bits in G["bf16_rne"]:
+        assert o.oracle_bf16_rne(f) == bits
+
+
+def test_host_sweep_port_results(o):
+    """The multi-threaded host sweep (the cpu_baseline 'port') produces the same data results."""
+    for mode in (1, 2, 4):
+        s, x = C.c_uint64(), C.c_uint32()
+        dt = o.oracle_host_sweep(1 << 22, 3, mode, 2, 0xB200, C.byref(s), C.byref(x))
+        assert dt > 0
+        assert (s.value, x.value) == _oracle.pattern_checksum(o, (1 << 22) // 4, 0xB200)
