@@ -1,8 +1,487 @@
-// placeholder — replaced by the tcgen05 kernel
+// tcgen05 tensor-core GEMM probe for sm_100a (no reference counterpart).
+//
+//   C[M][N] (bf16) = A[M][K] (bf16, K-major) * B[N][K]^T (bf16, K-major), fp32 accumulate in TMEM.
+//
+// Persistent, warp-specialised, one CTA per SM:
+//   warp 0   TMA producer   cp.async.bulk.tensor (SASS UTMALDG) 128B-swizzled A/B tiles -> smem ring
+//   warp 1   MMA issuer     one lane issues tcgen05.mma (SASS UTCHMMA) M=128 N=256 K=16, smem x smem -> TMEM
+//   warp 2   TMEM allocator tcgen05.alloc 512 columns = two 128x256 fp32 accumulators (double buffer)
+//   warps 4-7 epilogue      tcgen05.ld (LDTM) 32 lanes x 32 columns -> cvt bf16 -> global
+// Pipelines: smem full/empty mbarriers (TMA <-> MMA), TMEM full/empty mbarriers (MMA <-> epilogue),
+// so the epilogue of tile i overlaps the MMAs of tile i+1.
+//
+// Roofline: tensor bound.  Algorithmic work per launch: 2*M*N*K flop.
+// Operands come from a closed-form generator whose values (k/128, k integer) make every partial
+// sum exactly representable in fp32, so C is bit-exact against the fp64 oracle after one bf16 RNE.
+#include <cuda.h>
+#include <cuda_bf16.h>
 #include <cuda_runtime.h>
+
+#include <algorithm>
+#include <vector>
+
 #include "common.h"
-extern "C" {
-int b200probe_gemm(int, const b200probe_gemm_cfg_t*, b200probe_gemm_result_t*) { b200::set_error("gemm probe not built yet"); return B200PROBE_ESTATE; }
-int b200probe_gemm_launch(int, const void*, const void*, void*, int, int, int, void*) { b200::set_error("gemm probe not built yet"); return B200PROBE_ESTATE; }
-int b200probe_gemm_fill(int, void*, uint64_t, uint32_t, int, void*) { b200::set_error("gemm probe not built yet"); return B200PROBE_ESTATE; }
+
+namespace {
+
+constexpr int BM = 128, BN = 256, BK = 64, UMMA_K = 16;
+constexpr int STAGES = 4;
+constexpr int A_STAGE_BYTES = BM * BK * 2;          // 16 KiB
+constexpr int B_STAGE_BYTES = BN * BK * 2;          // 32 KiB
+constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
+constexpr int NUM_THREADS = 256;
+constexpr int TMEM_COLS = 512;
+constexpr int GROUP_M = 16;                         // rasterisation: 16 m-tiles per band (L2 reuse)
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
 }
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(bar), "r"(parity)
+            : "memory");
+    } while (!done);
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst_smem, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst_smem),
+                 "l"((uint64_t)map), "r"(bar), "r"(c0), "r"(c1)
+                 : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+// D[tmem] (+)= A[smem desc] * B[smem desc]
+__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+        "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// all previously issued MMAs of this thread arrive on the mbarrier when they complete
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]),
+          "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]),
+          "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]),
+          "=r"(v[31])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major operand tile [rows][64 bf16] written by TMA with SWIZZLE_128B: 8-row x 128-byte atoms,
+// 1024 bytes apart (SBO); LBO is unused for swizzled K-major layouts; descriptor version 1 (sm_100).
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
+    uint64_t d = (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+    d |= (uint64_t)1 << 16;                     // leading byte offset (ignored)
+    d |= (uint64_t)(1024 >> 4) << 32;           // stride byte offset
+    d |= (uint64_t)1 << 46;                     // version
+    d |= (uint64_t)2 << 61;                     // SWIZZLE_128B
+    return d;
+}
+// kind::f16 instruction descriptor: D=f32, A=B=bf16, both K-major, N>>3 at [17,23), M>>4 at [24,29)
+constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+
+struct TileCoord { int m0, n0; };
+__device__ __forceinline__ TileCoord tile_coord(int t, int num_m, int num_n) {
+    const int per_band = GROUP_M * num_n;
+    const int band = t / per_band;
+    const int first_m = band * GROUP_M;
+    const int rows = min(GROUP_M, num_m - first_m);
+    const int in_band = t - band * per_band;
+    return {(first_m + in_band % rows) * BM, (in_band / rows) * BN};
+}
+
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, __nv_bfloat16* __restrict__ C,
+                    int M, int N, int K) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint8_t* smem_a = smem;
+    uint8_t* smem_b = smem + STAGES * A_STAGE_BYTES;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+    uint64_t* full = bars;                  // [STAGES]
+    uint64_t* empty = bars + STAGES;        // [STAGES]
+    uint64_t* tfull = bars + 2 * STAGES;    // [2]
+    uint64_t* tempty = tfull + 2;           // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int num_m = M / BM, num_n = N / BN, num_tiles = num_m * num_n, num_kb = K / BK;
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tma_a) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tma_b) : "memory");
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < STAGES; ++s) { mbar_init(smem_u32(&full[s]), 1); mbar_init(smem_u32(&empty[s]), 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(smem_u32(&tfull[a]), 1); mbar_init(smem_u32(&tempty[a]), 4); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {                                   // ===== TMA producer =====
+            uint32_t stage = 0, phase = 0;
+            for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+                const TileCoord tc = tile_coord(t, num_m, num_n);
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    mbar_wait(smem_u32(&empty[stage]), phase ^ 1);
+                    const uint32_t fb = smem_u32(&full[stage]);
+                    mbar_expect_tx(fb, STAGE_BYTES);
+                    tma_load_2d(smem_u32(smem_a + stage * A_STAGE_BYTES), &tma_a, fb, kb * BK, tc.m0);
+                    tma_load_2d(smem_u32(smem_b + stage * B_STAGE_BYTES), &tma_b, fb, kb * BK, tc.n0);
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {                                   // ===== MMA issuer =====
+            uint32_t stage = 0, phase = 0, it = 0;
+            for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
+                const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
+                mbar_wait(smem_u32(&tempty[acc]), acc_phase ^ 1);      // epilogue drained this accumulator
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + acc * BN;
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    mbar_wait(smem_u32(&full[stage]), phase);          // TMA bytes landed
+                    tc_fence_after();
+                    const uint64_t a_desc = make_smem_desc(smem_u32(smem_a + stage * A_STAGE_BYTES));
+                    const uint64_t b_desc = make_smem_desc(smem_u32(smem_b + stage * B_STAGE_BYTES));
+#pragma unroll
+                    for (int k = 0; k < BK / UMMA_K; ++k) {
+                        // +32 bytes per K=16 step inside the 128-byte swizzle atom (address field is >>4)
+                        umma_bf16(d_tmem, a_desc + (uint64_t)(k * 2), b_desc + (uint64_t)(k * 2), kIdesc, (kb | k) != 0);
+                    }
+                    umma_commit(smem_u32(&empty[stage]));              // smem slot free when these MMAs retire
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+                umma_commit(smem_u32(&tfull[acc]));                    // accumulator ready for the epilogue
+            }
+        }
+    } else if (warp >= 4) {                                // ===== epilogue =====
+        const int q = warp - 4;                            // == warp % 4: the TMEM lane quadrant this warp may read
+        uint32_t it = 0;
+        for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
+            const TileCoord tc = tile_coord(t, num_m, num_n);
+            const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
+            mbar_wait(smem_u32(&tfull[acc]), acc_phase);
+            tc_fence_after();
+            const int row = tc.m0 + q * 32 + lane;
+            __nv_bfloat16* crow = C + (size_t)row * N + tc.n0;
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN;
+#pragma unroll 1
+            for (int c = 0; c < BN / 32; ++c) {
+                uint32_t v[32];
+                tmem_ld_32x32(taddr + c * 32, v);
+                tmem_ld_wait();
+                uint32_t pk[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    __nv_bfloat162 h = __floats2bfloat162_rn(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]));
+                    pk[j] = *reinterpret_cast<uint32_t*>(&h);
+                }
+                uint4* dst = reinterpret_cast<uint4*>(crow + c * 32);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) dst[j] = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_u32(&tempty[acc]));
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
+    }
+}
+
+__global__ void gemm_fill_kernel(uint16_t* dst, uint64_t elems, uint32_t seed, int which) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (; i < elems; i += stride) dst[i] = b200_gemm_elem_bits(i, seed, which);
+}
+
+__global__ void gather_kernel(const uint16_t* c, const uint64_t* idx, uint16_t* out, int n) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = c[idx[i]];
+}
+
+// ---- tensor maps (driver entry point fetched through the runtime: no link-time libcuda dependency) ----
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+int get_encode(EncodeTiledFn* fn) {
+    static EncodeTiledFn cached = nullptr;
+    if (!cached) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q);
+        if (e != cudaSuccess || q != cudaDriverEntryPointSuccess || !p) {
+            b200::set_error("cuTensorMapEncodeTiled unavailable (%s)", cudaGetErrorString(e));
+            return e != cudaSuccess ? b200::cuda_rc(e) : B200PROBE_ENOCUDA;
+        }
+        cached = (EncodeTiledFn)p;
+    }
+    *fn = cached;
+    return 0;
+}
+
+// [rows][k] bf16 row-major -> box {64 (k), box_rows}, 128B swizzle
+int make_map(CUtensorMap* map, const void* base, int rows, int k, int box_rows) {
+    EncodeTiledFn enc;
+    int rc = get_encode(&enc);
+    if (rc) return rc;
+    cuuint64_t dims[2] = {(cuuint64_t)k, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)k * 2};
+    cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { b200::set_error("cuTensorMapEncodeTiled failed: CUresult %d", (int)r); return B200PROBE_CUDA_BASE + 1; }
+    return 0;
+}
+
+int check_shape(int m, int n, int k) {
+    if (m <= 0 || n <= 0 || k <= 0 || m % BM || n % BN || k % BK) {
+        b200::set_error("gemm: m,n,k must be positive multiples of %d,%d,%d (got %d,%d,%d)", BM, BN, BK, m, n, k);
+        return B200PROBE_EINVAL;
+    }
+    return 0;
+}
+
+double median_f(std::vector<float> v) {
+    std::sort(v.begin(), v.end());
+    size_t n = v.size();
+    return n & 1 ? v[n / 2] : 0.5 * (v[n / 2 - 1] + v[n / 2]);
+}
+
+float bf16_bits_to_float(uint16_t b) {
+    uint32_t u = (uint32_t)b << 16;
+    float f;
+    memcpy(&f, &u, 4);
+    return f;
+}
+uint16_t float_to_bf16_rne(float f) {
+    uint32_t u;
+    memcpy(&u, &f, 4);
+    uint32_t r = 0x7fffu + ((u >> 16) & 1u);
+    return (uint16_t)((u + r) >> 16);
+}
+
+struct GemmBufs {
+    void *a = nullptr, *b = nullptr, *c = nullptr, *idx = nullptr, *out = nullptr;
+    unsigned long long* partials = nullptr;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    ~GemmBufs() {
+        if (a) cudaFree(a);
+        if (b) cudaFree(b);
+        if (c) cudaFree(c);
+        if (idx) cudaFree(idx);
+        if (out) cudaFree(out);
+        if (partials) cudaFree(partials);
+        if (e0) cudaEventDestroy(e0);
+        if (e1) cudaEventDestroy(e1);
+        if (stream) cudaStreamDestroy(stream);
+    }
+};
+
+}  // namespace
+
+extern "C" {
+
+int b200probe_gemm_fill(int ordinal, void* dst, uint64_t elems, uint32_t seed, int which, void* stream) {
+    b200::DevProps props;
+    int rc = b200::device_props(ordinal, &props);
+    if (rc) return rc;
+    if (!dst || (which != 0 && which != 1)) return B200PROBE_EINVAL;
+    B200_CUDA_TRY(cudaSetDevice(ordinal));
+    if (elems) gemm_fill_kernel<<<props.sms * 8, 256, 0, (cudaStream_t)stream>>>((uint16_t*)dst, elems, seed, which);
+    B200_CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+int b200probe_gemm_launch(int ordinal, const void* a, const void* b, void* c, int m, int n, int k, void* stream) {
+    b200::DevProps props;
+    int rc = b200::device_props(ordinal, &props);
+    if (rc) return rc;
+    rc = check_shape(m, n, k);
+    if (rc) return rc;
+    if (!a || !b || !c || (((uintptr_t)a | (uintptr_t)b | (uintptr_t)c) & 15)) { b200::set_error("gemm: operands must be 16-byte aligned device pointers"); return B200PROBE_EINVAL; }
+    B200_CUDA_TRY(cudaSetDevice(ordinal));
+    CUtensorMap ma, mb;
+    rc = make_map(&ma, a, m, k, BM);
+    if (rc) return rc;
+    rc = make_map(&mb, b, n, k, BN);
+    if (rc) return rc;
+    static bool attr_set[B200PROBE_MAX_DEVICES] = {false};
+    if (!attr_set[ordinal]) {
+        B200_CUDA_TRY(cudaFuncSetAttribute(gemm_bf16_tn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        attr_set[ordinal] = true;
+    }
+    const int tiles = (m / BM) * (n / BN);
+    const int grid = std::min(tiles, props.sms);
+    gemm_bf16_tn_kernel<<<grid, NUM_THREADS, SMEM_BYTES, (cudaStream_t)stream>>>(ma, mb, (__nv_bfloat16*)c, m, n, k);
+    B200_CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+int b200probe_gemm(int idx, const b200probe_gemm_cfg_t* cfg_in, b200probe_gemm_result_t* out) {
+    if (!out) return B200PROBE_EINVAL;
+    int ordinal = -1;
+    int rc = b200::cuda_ordinal_of(idx, &ordinal);
+    if (rc) return rc;
+    b200::DevProps props;
+    rc = b200::device_props(ordinal, &props);
+    if (rc) return rc;
+    b200probe_gemm_cfg_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    if (cfg_in) cfg = *cfg_in;
+    if (!cfg.m) cfg.m = 8192;
+    if (!cfg.n) cfg.n = 8192;
+    if (!cfg.k) cfg.k = 8192;
+    if (!cfg.warmup && !cfg.reps) { cfg.warmup = 3; cfg.reps = 10; }
+    if (cfg.reps < 1) cfg.reps = 1;
+    if (!cfg.seed) cfg.seed = 0xB200u;
+    if (!cfg.samples) cfg.samples = 1024;
+    rc = check_shape(cfg.m, cfg.n, cfg.k);
+    if (rc) return rc;
+    const int M = cfg.m, N = cfg.n, K = cfg.k;
+    memset(out, 0, sizeof(*out));
+    out->m = M; out->n = N; out->k = K;
+    out->verified = -1;
+
+    B200_CUDA_TRY(cudaSetDevice(ordinal));
+    GemmBufs g;
+    B200_CUDA_TRY(cudaStreamCreateWithFlags(&g.stream, cudaStreamNonBlocking));
+    B200_CUDA_TRY(cudaEventCreate(&g.e0));
+    B200_CUDA_TRY(cudaEventCreate(&g.e1));
+    B200_CUDA_TRY(cudaMalloc(&g.a, (size_t)M * K * 2));
+    B200_CUDA_TRY(cudaMalloc(&g.b, (size_t)N * K * 2));
+    B200_CUDA_TRY(cudaMalloc(&g.c, (size_t)M * N * 2));
+    B200_CUDA_TRY(cudaMalloc(&g.partials, 16));
+    B200_CUDA_TRY(cudaMemsetAsync(g.c, 0xFF, (size_t)M * N * 2, g.stream));
+    rc = b200probe_gemm_fill(ordinal, g.a, (uint64_t)M * K, cfg.seed, 0, g.stream);
+    if (rc) return rc;
+    rc = b200probe_gemm_fill(ordinal, g.b, (uint64_t)N * K, cfg.seed, 1, g.stream);
+    if (rc) return rc;
+
+    std::vector<float> ms((size_t)cfg.reps);
+    for (int it = -cfg.warmup; it < cfg.reps; ++it) {
+        if (it >= 0) B200_CUDA_TRY(cudaEventRecord(g.e0, g.stream));
+        rc = b200probe_gemm_launch(ordinal, g.a, g.b, g.c, M, N, K, g.stream);
+        if (rc) return rc;
+        if (it >= 0) {
+            B200_CUDA_TRY(cudaEventRecord(g.e1, g.stream));
+            B200_CUDA_TRY(cudaEventSynchronize(g.e1));
+            B200_CUDA_TRY(cudaEventElapsedTime(&ms[it], g.e0, g.e1));
+        }
+    }
+    B200_CUDA_TRY(cudaStreamSynchronize(g.stream));
+    const double flop = 2.0 * M * N * (double)K;
+    out->ms_median = median_f(ms);
+    out->ms_best = *std::min_element(ms.begin(), ms.end());
+    out->tflops_median = flop / (out->ms_median * 1e-3) / 1e12;
+    out->tflops_best = flop / (out->ms_best * 1e-3) / 1e12;
+
+    if (cfg.sustain_seconds > 0) {
+        // back-to-back launches for the requested wall time (power-capped steady state)
+        int batch = std::max(1, (int)(0.25 / (out->ms_median * 1e-3)));
+        double total_ms = 0, total_n = 0;
+        while (total_ms * 1e-3 < cfg.sustain_seconds) {
+            float t;
+            B200_CUDA_TRY(cudaEventRecord(g.e0, g.stream));
+            for (int i = 0; i < batch; ++i) {
+                rc = b200probe_gemm_launch(ordinal, g.a, g.b, g.c, M, N, K, g.stream);
+                if (rc) return rc;
+            }
+            B200_CUDA_TRY(cudaEventRecord(g.e1, g.stream));
+            B200_CUDA_TRY(cudaEventSynchronize(g.e1));
+            B200_CUDA_TRY(cudaEventElapsedTime(&t, g.e0, g.e1));
+            total_ms += t; total_n += batch;
+        }
+        out->tflops_sustained = flop * total_n / (total_ms * 1e-3) / 1e12;
+    }
+
+    // data result: checksum of C (run-to-run identity) + sampled outputs against fp64 dot products
+    B200_CUDA_TRY(cudaMemsetAsync(g.partials, 0, 16, g.stream));
+    rc = b200probe_hbm_read(ordinal, g.c, (uint64_t)M * N * 2, (uint64_t*)g.partials, nullptr, g.stream);
+    if (rc) return rc;
+    unsigned long long h[2];
+    B200_CUDA_TRY(cudaMemcpyAsync(h, g.partials, 16, cudaMemcpyDeviceToHost, g.stream));
+    const int S = cfg.samples;
+    std::vector<uint64_t> idxs((size_t)S);
+    for (int i = 0; i < S; ++i) {
+        // corners and tile seams first, then a hash-scattered set
+        uint32_t r, c;
+        if (i < 4) { r = (i & 1) ? M - 1 : 0; c = (i & 2) ? N - 1 : 0; }
+        else if (i < 8) { r = (i & 1) ? BM : BM - 1; c = (i & 2) ? BN : BN - 1; r = std::min<uint32_t>(r, M - 1); c = std::min<uint32_t>(c, N - 1); }
+        else { r = b200_mix32(cfg.seed ^ (0x9E37u * i)) % (uint32_t)M; c = b200_mix32(cfg.seed + 77u * i + 1) % (uint32_t)N; }
+        idxs[i] = (uint64_t)r * N + c;
+    }
+    B200_CUDA_TRY(cudaMalloc(&g.idx, (size_t)S * 8));
+    B200_CUDA_TRY(cudaMalloc(&g.out, (size_t)S * 2));
+    B200_CUDA_TRY(cudaMemcpyAsync(g.idx, idxs.data(), (size_t)S * 8, cudaMemcpyHostToDevice, g.stream));
+    gather_kernel<<<(S + 255) / 256, 256, 0, g.stream>>>((const uint16_t*)g.c, (const uint64_t*)g.idx, (uint16_t*)g.out, S);
+    B200_CUDA_TRY(cudaGetLastError());
+    std::vector<uint16_t> got((size_t)S);
+    B200_CUDA_TRY(cudaMemcpyAsync(got.data(), g.out, (size_t)S * 2, cudaMemcpyDeviceToHost, g.stream));
+    B200_CUDA_TRY(cudaStreamSynchronize(g.stream));
+    out->c_sum64 = h[0];
+    out->c_xor32 = (uint32_t)h[1];
+    int bad = 0;
+    double max_abs = 0, max_rel = 0;
+    for (int i = 0; i < S; ++i) {
+        const uint64_t r = idxs[i] / N, c = idxs[i] % N;
+        double acc = 0;
+        for (int k = 0; k < K; ++k)
+            acc += (double)bf16_bits_to_float(b200_gemm_elem_bits(r * K + k, cfg.seed, 0)) * (double)bf16_bits_to_float(b200_gemm_elem_bits(c * K + k, cfg.seed, 1));
+        const uint16_t want = float_to_bf16_rne((float)acc);
+        const double gotf = bf16_bits_to_float(got[i]);
+        const double err = fabs(gotf - acc);
+        max_abs = std::max(max_abs, err);
+        if (acc != 0) max_rel = std::max(max_rel, err / fabs(acc));
+        if (got[i] != want) ++bad;      // bit-exact bar: operands make every partial sum exact in fp32
+    }
+    out->samples = S; out->bad = bad;
+    out->max_abs_err = max_abs; out->max_rel_err = max_rel;
+    out->verified = bad == 0 ? 1 : 0;
+    if (bad) {
+        b200::set_error("gemm: %d of %d sampled outputs differ from the fp64 contraction rounded to bf16 (max abs err %g)", bad, S, max_abs);
+        return B200PROBE_EMISMATCH;
+    }
+    return 0;
+}
+
+}  // extern "C"

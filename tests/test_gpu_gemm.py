@@ -1,0 +1,81 @@
+"""GPU parity for the tcgen05 GEMM probe: bit-exact against the fp64 oracle contraction rounded
+once to bf16 (operands k/128 make every fp32 partial sum exact; tolerance = 0 ulp, stated here)."""
+import numpy as np
+import pytest
+
+import _oracle
+
+pytestmark = pytest.mark.gpu
+SEED = 0xB200
+
+
+@pytest.fixture(scope="module")
+def env():
+    import torch
+
+    from k3s_nvidia_b200.probe import Probe
+
+    assert torch.cuda.is_available()
+    return torch, Probe(), _oracle.load()
+
+
+def oracle_operands(o, rows, k, which, seed=SEED):
+    """integer numerators (value = n/128), from the oracle's element function"""
+    out = np.empty((rows, k), dtype=np.int64)
+    for r in range(rows):
+        for c in range(k):
+            out[r, c] = int(round(o.oracle_gemm_elem(r * k + c, seed, which) * 128))
+    return out
+
+
+def bf16_bits(f32):
+    u = f32.astype(np.float32).view(np.uint32).astype(np.uint64)
+    r = 0x7FFF + ((u >> 16) & 1)
+    return ((u + r) >> 16).astype(np.uint16)
+
+
+@pytest.mark.parametrize("m,n,k", [(128, 256, 64), (256, 512, 128), (384, 256, 320), (128, 768, 1024)])
+def test_whole_matrix_bit_exact_vs_oracle(env, m, n, k):
+    torch, p, o = env
+    st = torch.cuda.current_stream().cuda_stream
+    a = torch.empty(m * k, dtype=torch.int16, device="cuda:0")
+    b = torch.empty(n * k, dtype=torch.int16, device="cuda:0")
+    c = torch.full((m * n,), -1, dtype=torch.int16, device="cuda:0")
+    p._check(p.lib.b200probe_gemm_fill(0, a.data_ptr(), m * k, SEED, 0, st), "fill A")
+    p._check(p.lib.b200probe_gemm_fill(0, b.data_ptr(), n * k, SEED, 1, st), "fill B")
+    p._check(p.lib.b200probe_gemm_launch(0, a.data_ptr(), b.data_ptr(), c.data_ptr(), m, n, k, st), "gemm")
+    torch.cuda.synchronize()
+    # operands: device generator == oracle generator, bit for bit
+    A = oracle_operands(o, m, k, 0)
+    B = oracle_operands(o, n, k, 1)
+    got_a = a.cpu().numpy().view(np.uint16).reshape(m, k)
+    assert np.array_equal(got_a, bf16_bits((A / 128.0).astype(np.float32)))
+    assert got_a[0, 0] == o.oracle_gemm_elem_bits(0, SEED, 0)
+    # contraction: exact integer arithmetic, one rounding
+    want = bf16_bits(((A @ B.T).astype(np.float64) / 16384.0).astype(np.float32))
+    got = c.cpu().numpy().view(np.uint16).reshape(m, n)
+    bad = np.argwhere(got != want)
+    assert bad.size == 0, f"{len(bad)} mismatches, first at {bad[:5].tolist()}"
+
+
+def test_headline_size_sampled_and_stable(env):
+    """BASELINE GEMM probe at M=N=K=8192: 1024 sampled outputs bit-exact vs fp64 (checked inside the
+    library AND here against the oracle for a few), checksum of C identical run to run, TFLOP/s
+    stable within 1% (north_star's run-to-run bound)."""
+    torch, p, o = env
+    r1 = p.gemm(0, warmup=3, reps=10)
+    r2 = p.gemm(0, warmup=3, reps=10)
+    assert r1.verified == 1 and r1.bad == 0 and r1.samples == 1024 and r1.max_abs_err < 0.5
+    assert (r1.c_sum64, r1.c_xor32) == (r2.c_sum64, r2.c_xor32)
+    assert abs(r1.tflops_median - r2.tflops_median) / r1.tflops_median < 0.02
+    assert r1.tflops_median > 100
+
+
+def test_bad_shapes_fail_loudly(env):
+    torch, p, o = env
+    from k3s_nvidia_b200.probe import ProbeError
+
+    with pytest.raises(ProbeError):
+        p.gemm(0, m=100, n=256, k=64)
+    with pytest.raises(ProbeError):
+        p.gemm(0, m=128, n=256, k=72)
