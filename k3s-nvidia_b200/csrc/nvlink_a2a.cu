@@ -164,6 +164,18 @@ int b200probe_enable_peer_access(const int* ordinals, int g) {
         int rc = b200::device_props(ordinals[i], &props);
         if (rc) return rc;
         B200_CUDA_TRY(cudaSetDevice(ordinals[i]));
+        for (int j = 0; j < g; ++j) {
+            if (i == j) continue;
+            int can = 0;
+            B200_CUDA_TRY(cudaDeviceCanAccessPeer(&can, ordinals[i], ordinals[j]));
+            if (!can) { b200::set_error("no peer access %d -> %d", ordinals[i], ordinals[j]); return B200PROBE_ENOPEER; }
+            cudaError_t e = cudaDeviceEnablePeerAccess(ordinals[j], 0);
+            if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) {
+                b200::set_error("cudaDeviceEnablePeerAccess(%d -> %d): %s", ordinals[i], ordinals[j], cudaGetErrorString(e));
+                return b200::cuda_rc(e);
+            }
+            cudaGetLastError();   // clear cudaErrorPeerAccessAlreadyEnabled
+        }
     }
     return 0;
 }
