@@ -29,6 +29,7 @@ GIB = 1 << 30
 METRIC = "health-probe HBM GB/s & NVLink GB/s vs peak per GPU at 1/2/4/8 B200"
 WORKLOAD = "configs[1]: single-B200 HBM bandwidth probe, copy pass at the 1 GiB verdict size of the 1 MiB-1 GiB sweep"
 NVLINK_NOMINAL = 900.0
+A2A_VARIANT = int(os.environ.get("B200PROBE_A2A_VARIANT", "0"))   # 0 = TMA bulk stores to the peer, 1 = 16-byte stores
 NVLINK_MEASURED = 770.0   # /opt/skills/guides/B200_PROFILING.md, peer copy per direction
 
 
@@ -345,7 +346,7 @@ def nvlink_exchange(torch, D, p, local_rank, rank, world, stream, args):
     steps = max(3, min(args.steps, 20))
 
     def push():
-        p._check(lib.b200probe_a2a_push(local_rank, rank, world, peers, S, seed, 0, stream), "a2a_push")
+        p._check(lib.b200probe_a2a_push(local_rank, rank, world, peers, S, seed, 0, A2A_VARIANT, stream), "a2a_push")
 
     for _ in range(3):
         push()
@@ -385,7 +386,7 @@ def nvlink_exchange(torch, D, p, local_rank, rank, world, stream, args):
     return {"bytes_per_pair": S, "ms_per_exchange": round(ms, 4), "egress_gbs_per_gpu": round(per_dir, 1),
             "aggregate_gbs": round(per_dir * world, 1), "frac_of_nominal_900": round(per_dir / NVLINK_NOMINAL, 4),
             "frac_of_measured_770": round(per_dir / NVLINK_MEASURED, 4), "verified": bool(ok), "steps": steps,
-            "kernel": "a2a_push_kernel (16-byte stores on IPC peer-mapped windows; local slot included)",
+            "kernel": ("a2a_ring_push_kernel (cp.async.bulk stores to IPC peer-mapped windows)" if A2A_VARIANT == 0 else "a2a_push_kernel (16-byte stores on IPC peer-mapped windows)") + "; local slot included",
             "algorithmic_bytes_per_gpu_per_direction": (world - 1) * S}
 
 

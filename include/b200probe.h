@@ -182,6 +182,7 @@ typedef struct b200probe_a2a_cfg {
     uint32_t seed;
     int      verify;
     int      ctas_per_peer;         /* 0 = default                                                 */
+    int      variant;               /* B200PROBE_VARIANT_TMA (bulk stores to the peer) or _DIRECT   */
 } b200probe_a2a_cfg_t;
 
 typedef struct b200probe_a2a_result {
@@ -214,11 +215,11 @@ int b200probe_a2a_window_release(int cuda_ordinal, void* window, int imported);
  * generated in registers and stored over NVLink; slot `rank` of the local window gets the local
  * chunk.  Asynchronous on `stream`. */
 int b200probe_a2a_push(int cuda_ordinal, int rank, int world, void* const* peer_windows,
-                       uint64_t bytes_per_pair, uint32_t seed, int ctas_per_peer, void* stream);
+                       uint64_t bytes_per_pair, uint32_t seed, int ctas_per_peer, int variant, void* stream);
 /* Push from a resident send buffer [world][S] (copy over NVLink instead of generate). */
 int b200probe_a2a_push_buf(int cuda_ordinal, int rank, int world, const void* sendbuf,
                            void* const* peer_windows, uint64_t bytes_per_pair,
-                           int ctas_per_peer, void* stream);
+                           int ctas_per_peer, int variant, void* stream);
 /* Seed of the chunk rank `src` sends to rank `dst`. */
 uint32_t b200probe_a2a_chunk_seed(uint32_t seed, int src, int dst);
 

@@ -95,6 +95,7 @@ class A2aCfg(C.Structure):
         ("seed", C.c_uint32),
         ("verify", C.c_int),
         ("ctas_per_peer", C.c_int),
+        ("variant", C.c_int),
     ]
 
 
@@ -173,8 +174,8 @@ SIGNATURES = {
     "b200probe_a2a_window_create": (C.c_int, [C.c_int, C.c_int, C.c_uint64, _P(_vp), C.c_char_p]),
     "b200probe_a2a_window_import": (C.c_int, [C.c_int, C.c_char_p, _P(_vp)]),
     "b200probe_a2a_window_release": (C.c_int, [C.c_int, _vp, C.c_int]),
-    "b200probe_a2a_push": (C.c_int, [C.c_int, C.c_int, C.c_int, _P(_vp), C.c_uint64, C.c_uint32, C.c_int, _vp]),
-    "b200probe_a2a_push_buf": (C.c_int, [C.c_int, C.c_int, C.c_int, _vp, _P(_vp), C.c_uint64, C.c_int, _vp]),
+    "b200probe_a2a_push": (C.c_int, [C.c_int, C.c_int, C.c_int, _P(_vp), C.c_uint64, C.c_uint32, C.c_int, C.c_int, _vp]),
+    "b200probe_a2a_push_buf": (C.c_int, [C.c_int, C.c_int, C.c_int, _vp, _P(_vp), C.c_uint64, C.c_int, C.c_int, _vp]),
     "b200probe_a2a_chunk_seed": (C.c_uint32, [C.c_uint32, C.c_int, C.c_int]),
     "b200probe_gemm": (C.c_int, [C.c_int, _P(GemmCfg), _P(GemmResult)]),
     "b200probe_gemm_launch": (C.c_int, [C.c_int, _vp, _vp, _vp, C.c_int, C.c_int, C.c_int, _vp]),

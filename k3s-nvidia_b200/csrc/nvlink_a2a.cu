@@ -14,6 +14,7 @@
 #include <vector>
 
 #include "common.h"
+#include "ptx.cuh"
 
 namespace {
 
@@ -67,10 +68,91 @@ __global__ void __launch_bounds__(512) a2a_push_kernel(PeerTable peers, const ui
     }
 }
 
+
+// TMA variant: each warp owns a ring of shared-memory stages, generates (or bulk-loads) a chunk
+// into a stage and bulk-stores it (cp.async.bulk shared->global, SASS UBLKCP) to the PEER window:
+// the copy engine of the SM streams whole 8-32 KiB bursts into NVLink instead of 16-byte stores.
+constexpr int kRingWarps = 4, kRingMaxStages = 8;
+template <bool FROM_BUF>
+__global__ void __launch_bounds__(kRingWarps * 32) a2a_ring_push_kernel(PeerTable peers, const uint8_t* __restrict__ sendbuf, int rank, int world,
+                                                                         uint64_t S, uint32_t seed, int ctas_per_peer, int only_dst,
+                                                                         uint32_t SB, uint32_t NS) {
+    using namespace b200ptx;
+    extern __shared__ __align__(128) uint8_t smem[];
+    __shared__ __align__(8) uint64_t full_bar[kRingWarps * kRingMaxStages];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < kRingWarps * kRingMaxStages; ++i) mbar_init(smem_u32(&full_bar[i]), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    const int dst = blockIdx.x / ctas_per_peer;
+    if (dst >= world) return;
+    if (only_dst >= 0 && dst != only_dst) return;
+    if (only_dst == -2 && dst == rank) return;
+    const int sub = blockIdx.x % ctas_per_peer;
+    uint8_t* out = peers.win[dst] + (uint64_t)rank * S;
+    const uint8_t* in = sendbuf + (uint64_t)dst * S;
+    const uint32_t cs = chunk_seed(seed, rank, dst);
+    const uint64_t nchunks = (S + SB - 1) / SB;
+    const uint64_t worker = (uint64_t)sub * kRingWarps + warp, nworkers = (uint64_t)ctas_per_peer * kRingWarps;
+    const uint64_t n_my = worker < nchunks ? (nchunks - worker + nworkers - 1) / nworkers : 0;
+    const uint32_t ring = smem_u32(smem) + warp * NS * SB;
+    uint8_t* ring_ptr = smem + (size_t)warp * NS * SB;
+    const uint32_t bar0 = smem_u32(&full_bar[warp * kRingMaxStages]);
+    const uint64_t pol = policy_evict_first();
+    auto off_of = [&](uint64_t k) { return (worker + k * nworkers) * (uint64_t)SB; };
+    auto len_of = [&](uint64_t k) { return (uint32_t)min((uint64_t)SB, S - off_of(k)); };
+    uint32_t cs_stage = 0, cph = 0;
+    if (FROM_BUF) {
+        if (lane == 0 && n_my > 0) {     // bulk-load local chunk, bulk-store to the peer; registers untouched
+            uint64_t issued = 0;
+            uint32_t ps = 0;
+            auto load_next = [&]() {
+                const uint32_t len = len_of(issued);
+                mbar_expect_tx(bar0 + ps * 8, len);
+                bulk_g2s(ring + ps * SB, in + off_of(issued), len, bar0 + ps * 8, pol);
+                ++issued;
+                if (++ps == NS) ps = 0;
+            };
+            const uint64_t ahead = min((uint64_t)(NS - 1), n_my);
+            while (issued < ahead) load_next();
+            for (uint64_t k = 0; k < n_my; ++k) {
+                mbar_wait(bar0 + cs_stage * 8, cph);
+                bulk_s2g(out + off_of(k), ring + cs_stage * SB, len_of(k), pol);
+                bulk_commit();
+                if (issued < n_my) { bulk_wait_read<1>(); load_next(); }
+                if (++cs_stage == NS) { cs_stage = 0; cph ^= 1; }
+            }
+            bulk_wait_all();
+        }
+    } else {
+        for (uint64_t k = 0; k < n_my; ++k) {
+            if (k >= NS) {
+                if (lane == 0) bulk_wait_read_dyn((int)NS - 1);
+                __syncwarp();
+            }
+            uint4* st = reinterpret_cast<uint4*>(ring_ptr + (size_t)cs_stage * SB);
+            const uint32_t nvec = len_of(k) >> 4;
+            const uint64_t w0 = off_of(k) >> 2;
+#pragma unroll 4
+            for (uint32_t i = lane; i < nvec; i += 32) {
+                const uint64_t w = w0 + (uint64_t)i * 4;
+                st[i] = make_uint4(b200_pattern_word(w, cs), b200_pattern_word(w + 1, cs), b200_pattern_word(w + 2, cs), b200_pattern_word(w + 3, cs));
+            }
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) { bulk_s2g(out + off_of(k), ring + cs_stage * SB, len_of(k), pol); bulk_commit(); }
+            if (++cs_stage == NS) cs_stage = 0;
+        }
+        if (lane == 0) bulk_wait_all();
+    }
+}
+
 int default_ctas_per_peer(int sms, int world) { return std::max(1, (sms * 4 + world - 1) / world); }
 
 int launch_push(int ordinal, int rank, int world, void* const* windows, const void* sendbuf, uint64_t S, uint32_t seed, int ctas_per_peer,
-                int only_dst, cudaStream_t stream) {
+                int only_dst, int variant, cudaStream_t stream) {
     if (world < 1 || world > kMaxWorld || rank < 0 || rank >= world || !windows) { b200::set_error("a2a: bad rank/world"); return B200PROBE_EINVAL; }
     if (S & 15) { b200::set_error("a2a: bytes_per_pair must be a multiple of 16"); return B200PROBE_EINVAL; }
     b200::DevProps props;
@@ -81,7 +163,24 @@ int launch_push(int ordinal, int rank, int world, void* const* windows, const vo
     PeerTable t;
     memset(&t, 0, sizeof(t));
     for (int i = 0; i < world; ++i) t.win[i] = (uint8_t*)windows[i];
-    if (ctas_per_peer <= 0) ctas_per_peer = default_ctas_per_peer(props.sms, only_dst >= 0 ? 1 : world);
+    const int targets = only_dst >= 0 ? 1 : world;
+    if (variant == B200PROBE_VARIANT_TMA) {
+        // one CTA per SM in total, split over the destinations; 4 warps x 4 stages x 8 KiB per CTA
+        if (ctas_per_peer <= 0) ctas_per_peer = std::max(1, props.sms / targets);
+        const uint32_t SB = 8192, NS = 4;
+        const size_t smem = (size_t)kRingWarps * NS * SB;
+        static bool attr[2] = {false, false};
+        // per-device function attribute; cheap enough to set on every launch
+        if (sendbuf) B200_CUDA_TRY(cudaFuncSetAttribute(a2a_ring_push_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        else B200_CUDA_TRY(cudaFuncSetAttribute(a2a_ring_push_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        (void)attr;
+        dim3 g((unsigned)(world * ctas_per_peer));
+        if (sendbuf) a2a_ring_push_kernel<true><<<g, kRingWarps * 32, smem, stream>>>(t, (const uint8_t*)sendbuf, rank, world, S, seed, ctas_per_peer, only_dst, SB, NS);
+        else a2a_ring_push_kernel<false><<<g, kRingWarps * 32, smem, stream>>>(t, nullptr, rank, world, S, seed, ctas_per_peer, only_dst, SB, NS);
+        B200_CUDA_TRY(cudaGetLastError());
+        return 0;
+    }
+    if (ctas_per_peer <= 0) ctas_per_peer = default_ctas_per_peer(props.sms, targets);
     dim3 grid((unsigned)(world * ctas_per_peer));
     if (sendbuf) a2a_push_kernel<true><<<grid, 512, 0, stream>>>(t, (const uint8_t*)sendbuf, rank, world, S, seed, ctas_per_peer, only_dst);
     else a2a_push_kernel<false><<<grid, 512, 0, stream>>>(t, nullptr, rank, world, S, seed, ctas_per_peer, only_dst);
@@ -222,14 +321,15 @@ int b200probe_a2a_window_release(int ordinal, void* window, int imported) {
     return 0;
 }
 
-int b200probe_a2a_push(int ordinal, int rank, int world, void* const* windows, uint64_t S, uint32_t seed, int ctas_per_peer, void* stream) {
-    return launch_push(ordinal, rank, world, windows, nullptr, S, seed, ctas_per_peer, -1, (cudaStream_t)stream);
+int b200probe_a2a_push(int ordinal, int rank, int world, void* const* windows, uint64_t S, uint32_t seed, int ctas_per_peer, int variant,
+                       void* stream) {
+    return launch_push(ordinal, rank, world, windows, nullptr, S, seed, ctas_per_peer, -1, variant, (cudaStream_t)stream);
 }
 
 int b200probe_a2a_push_buf(int ordinal, int rank, int world, const void* sendbuf, void* const* windows, uint64_t S, int ctas_per_peer,
-                           void* stream) {
+                           int variant, void* stream) {
     if (!sendbuf) return B200PROBE_EINVAL;
-    return launch_push(ordinal, rank, world, windows, sendbuf, S, 0, ctas_per_peer, -1, (cudaStream_t)stream);
+    return launch_push(ordinal, rank, world, windows, sendbuf, S, 0, ctas_per_peer, -1, variant, (cudaStream_t)stream);
 }
 
 int b200probe_nvlink_a2a(const int* ordinals, int g, const b200probe_a2a_cfg_t* cfg_in, double* pair_gbs, b200probe_a2a_result_t* out) {
@@ -321,7 +421,7 @@ int b200probe_nvlink_a2a(const int* ordinals, int g, const b200probe_a2a_cfg_t* 
                 B200_CUDA_TRY(cudaSetDevice(p.ordinal));
                 if (timed) B200_CUDA_TRY(cudaEventRecord(p.e0, p.stream));
                 // -2: skip the local slot in the timed exchange (it is HBM traffic, not NVLink)
-                int rc = launch_push(p.ordinal, i, g, windows, nullptr, S, cfg.seed, cfg.ctas_per_peer, -2, p.stream);
+                int rc = launch_push(p.ordinal, i, g, windows, nullptr, S, cfg.seed, cfg.ctas_per_peer, -2, cfg.variant, p.stream);
                 if (rc) return rc;
                 if (timed) B200_CUDA_TRY(cudaEventRecord(p.e1, p.stream));
             }
@@ -350,7 +450,7 @@ int b200probe_nvlink_a2a(const int* ordinals, int g, const b200probe_a2a_cfg_t* 
                 std::vector<double> ts;
                 for (int it = -cfg.warmup; it < cfg.reps; ++it) {
                     if (it >= 0) B200_CUDA_TRY(cudaEventRecord(p.e0, p.stream));
-                    int rc = launch_push(p.ordinal, i, g, windows, nullptr, S, cfg.seed, cfg.ctas_per_peer, j, p.stream);
+                    int rc = launch_push(p.ordinal, i, g, windows, nullptr, S, cfg.seed, cfg.ctas_per_peer, j, cfg.variant, p.stream);
                     if (rc) return rc;
                     if (it >= 0) {
                         float ms;
@@ -368,7 +468,7 @@ int b200probe_nvlink_a2a(const int* ordinals, int g, const b200probe_a2a_cfg_t* 
         out->min_pair_gbs = mn; out->max_pair_gbs = mx;
         // the local slots are not written in pair mode; fill them so verification covers the window
         for (int i = 0; i < g; ++i) {
-            int rc = launch_push(ctx.d[i].ordinal, i, g, windows, nullptr, S, cfg.seed, cfg.ctas_per_peer, i, ctx.d[i].stream);
+            int rc = launch_push(ctx.d[i].ordinal, i, g, windows, nullptr, S, cfg.seed, cfg.ctas_per_peer, i, cfg.variant, ctx.d[i].stream);
             if (rc) return rc;
         }
         int rc = sync_all();
@@ -403,7 +503,7 @@ int b200probe_nvlink_a2a(const int* ordinals, int g, const b200probe_a2a_cfg_t* 
         out->min_pair_gbs = mn; out->max_pair_gbs = mx;
         if (!nccl_mode) {   // local slots (not part of the timed exchange)
             for (int i = 0; i < g; ++i) {
-                int rc = launch_push(ctx.d[i].ordinal, i, g, windows, nullptr, S, cfg.seed, cfg.ctas_per_peer, i, ctx.d[i].stream);
+                int rc = launch_push(ctx.d[i].ordinal, i, g, windows, nullptr, S, cfg.seed, cfg.ctas_per_peer, i, cfg.variant, ctx.d[i].stream);
                 if (rc) return rc;
             }
             int rc = sync_all();

@@ -25,7 +25,8 @@ def env():
 
 @pytest.mark.parametrize("S", [16, 4096 + 16, 1 << 20, (3 << 20) + 48])
 @pytest.mark.parametrize("from_buf", [False, True])
-def test_push_lands_oracle_pattern_in_every_peer_window(env, S, from_buf):
+@pytest.mark.parametrize("variant", [0, 1], ids=["tma", "direct"])
+def test_push_lands_oracle_pattern_in_every_peer_window(env, S, from_buf, variant):
     torch, p, o = env
     g = min(torch.cuda.device_count(), 8)
     ords = (C.c_int * g)(*range(g))
@@ -37,9 +38,9 @@ def test_push_lands_oracle_pattern_in_every_peer_window(env, S, from_buf):
         if from_buf:
             send = np.concatenate([_oracle.pattern(o, 0, S // 4, o.oracle_a2a_chunk_seed(SEED, r, d)) for d in range(g)])
             sb = torch.from_numpy(send.view(np.uint8)).to(f"cuda:{r}")
-            p._check(p.lib.b200probe_a2a_push_buf(r, r, g, sb.data_ptr(), peers, S, 0, st), "push_buf")
+            p._check(p.lib.b200probe_a2a_push_buf(r, r, g, sb.data_ptr(), peers, S, 0, variant, st), "push_buf")
         else:
-            p._check(p.lib.b200probe_a2a_push(r, r, g, peers, S, SEED, 3, st), "push")
+            p._check(p.lib.b200probe_a2a_push(r, r, g, peers, S, SEED, 3, variant, st), "push")
     for r in range(g):
         torch.cuda.synchronize(r)
     for dst in range(g):
@@ -52,11 +53,12 @@ def test_push_lands_oracle_pattern_in_every_peer_window(env, S, from_buf):
             assert p.lib.b200probe_a2a_chunk_seed(SEED, src, dst) == o.oracle_a2a_chunk_seed(SEED, src, dst)
 
 
+@pytest.mark.parametrize("variant", [0, 1], ids=["tma", "direct"])
 @pytest.mark.parametrize("mode", [0, 1, 2], ids=["peer-all", "peer-pair", "nccl"])
-def test_single_process_probe_verifies_and_reports(env, mode):
+def test_single_process_probe_verifies_and_reports(env, mode, variant):
     torch, p, o = env
     g = min(torch.cuda.device_count(), 8)
-    rep = p.nvlink_a2a(list(range(g)), bytes_per_pair=8 << 20, mode=mode, warmup=1, reps=3, verify=1)
+    rep = p.nvlink_a2a(list(range(g)), bytes_per_pair=8 << 20, mode=mode, warmup=1, reps=3, verify=1, variant=variant)
     assert rep.verified == 1 and rep.g == g
     for i in range(g):
         for j in range(g):
