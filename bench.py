@@ -29,7 +29,7 @@ GIB = 1 << 30
 METRIC = "health-probe HBM GB/s & NVLink GB/s vs peak per GPU at 1/2/4/8 B200"
 WORKLOAD = "configs[1]: single-B200 HBM bandwidth probe, copy pass at the 1 GiB verdict size of the 1 MiB-1 GiB sweep"
 NVLINK_NOMINAL = 900.0
-A2A_VARIANT = int(os.environ.get("B200PROBE_A2A_VARIANT", "0"))   # 0 = TMA bulk stores to the peer, 1 = 16-byte stores
+A2A_VARIANT = int(os.environ.get("B200PROBE_A2A_VARIANT", "0"))   # 0 PULL_TMA (default), 1 PUSH_TMA, 2 PUSH_DIRECT, 3 PUSH_BUF
 NVLINK_MEASURED = 770.0   # /opt/skills/guides/B200_PROFILING.md, peer copy per direction
 
 
@@ -326,13 +326,17 @@ def run_ours(args):
 
 
 def nvlink_exchange(torch, D, p, local_rank, rank, world, stream, args):
-    """configs[2]: every rank pushes (world-1) chunks of S bytes into its peers' IPC-mapped windows
-    with our peer-store kernel; device-timed, max over ranks; landed data verified by checksum."""
+    """configs[2]: every rank owns a window [recv world x S][send world x S]; handles are exchanged
+    over torch.distributed (control data only) and every rank PULLS its peers' send chunks over
+    NVLink with our TMA kernel into its recv slots; device-timed, max over ranks; landed data verified."""
     S = 256 << 20
     lib = p.lib
+    seed = 0xB200
     win = C.c_void_p()
     handle = C.create_string_buffer(64)
     p._check(lib.b200probe_a2a_window_create(local_rank, world, S, C.byref(win), handle), "a2a_window_create")
+    p._check(lib.b200probe_a2a_window_fill(local_rank, win, rank, world, S, seed, stream), "a2a_window_fill")
+    torch.cuda.synchronize()
     handles = D.all_gather_bytes(handle.raw)
     peers = (C.c_void_p * world)()
     for r in range(world):
@@ -342,25 +346,28 @@ def nvlink_exchange(torch, D, p, local_rank, rank, world, stream, args):
             q = C.c_void_p()
             p._check(lib.b200probe_a2a_window_import(local_rank, handles[r], C.byref(q)), "a2a_window_import")
             peers[r] = q.value
-    seed = 0xB200
+    D.barrier()                      # every send half is filled before anyone pulls
     steps = max(3, min(args.steps, 20))
 
-    def push():
-        p._check(lib.b200probe_a2a_push(local_rank, rank, world, peers, S, seed, 0, A2A_VARIANT, stream), "a2a_push")
+    def exchange(only_peer=-2):
+        p._check(lib.b200probe_a2a_exchange(local_rank, rank, world, peers, S, seed, A2A_VARIANT, 0, only_peer, stream), "a2a_exchange")
 
     for _ in range(3):
-        push()
+        exchange()
     torch.cuda.synchronize()
     D.barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(steps):
-        push()
+        exchange()
     e1.record()
     torch.cuda.synchronize()
     D.barrier()
     ms = D.reduce_scalar(e0.elapsed_time(e1), "max") / steps
-    # verify what landed here: slot r must hold pattern(chunk_seed(seed, r, rank))
+    exchange(-1)                     # complete the window (local slot) for verification
+    torch.cuda.synchronize()
+    D.barrier()
+    # verify what landed here: recv slot r must hold pattern(chunk_seed(seed, r, rank))
     ok = 1.0
     part = torch.zeros(4, dtype=torch.int64, device=torch.device("cuda", local_rank))
     sys.path.insert(0, os.path.join(ROOT, "tests"))
@@ -383,11 +390,14 @@ def nvlink_exchange(torch, D, p, local_rank, rank, world, stream, args):
     D.barrier()
     lib.b200probe_a2a_window_release(local_rank, win, 0)
     per_dir = (world - 1) * S / (ms * 1e-3) / 1e9
-    return {"bytes_per_pair": S, "ms_per_exchange": round(ms, 4), "egress_gbs_per_gpu": round(per_dir, 1),
+    names = {0: "a2a_ring_kernel PULL (cp.async.bulk loads from IPC peer-mapped windows, bulk stores to local HBM)",
+             1: "a2a_ring_kernel PUSH (pattern in smem, cp.async.bulk stores to peer windows)",
+             2: "a2a_direct_kernel PUSH (16-byte stores on peer pointers)", 3: "a2a_ring_kernel PUSH_BUF"}
+    return {"bytes_per_pair": S, "ms_per_exchange": round(ms, 4), "gbs_per_gpu_per_direction": round(per_dir, 1),
             "aggregate_gbs": round(per_dir * world, 1), "frac_of_nominal_900": round(per_dir / NVLINK_NOMINAL, 4),
             "frac_of_measured_770": round(per_dir / NVLINK_MEASURED, 4), "verified": bool(ok), "steps": steps,
-            "kernel": ("a2a_ring_push_kernel (cp.async.bulk stores to IPC peer-mapped windows)" if A2A_VARIANT == 0 else "a2a_push_kernel (16-byte stores on IPC peer-mapped windows)") + "; local slot included",
-            "algorithmic_bytes_per_gpu_per_direction": (world - 1) * S}
+            "kernel": names.get(A2A_VARIANT, str(A2A_VARIANT)), "algorithmic_bytes_per_gpu_per_direction": (world - 1) * S,
+            "scaling": "every rank moves (world-1)*S per exchange: total work grows with N"}
 
 
 def main():

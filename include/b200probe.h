@@ -171,27 +171,33 @@ int b200probe_hbm_copy_host(int cuda_ordinal, const void* src_host, void* dst_ho
                             uint64_t* sum64, uint32_t* xor32);
 
 /* ---- NVLink all-to-all (row a12) --------------------------------------------------------------- */
-#define B200PROBE_A2A_PEER_ALL    0   /* peer-memory store kernel, all pairs concurrently          */
+#define B200PROBE_A2A_PEER_ALL    0   /* our peer-memory kernel, all pairs concurrently            */
 #define B200PROBE_A2A_PEER_PAIR   1   /* same kernel, one (src,dst) pair at a time -> matrix       */
 #define B200PROBE_A2A_NCCL        2   /* grouped ncclSend/ncclRecv (the library leg, for contrast) */
+/* exchange kernels (cfg.variant) */
+#define B200PROBE_A2A_PULL_TMA    0   /* bulk-LOAD the peers' send chunks over NVLink (default: reads
+                                         move 781 GB/s per direction on B200, writes 712)           */
+#define B200PROBE_A2A_PUSH_TMA    1   /* generate in shared memory, bulk-STORE into the peers       */
+#define B200PROBE_A2A_PUSH_DIRECT 2   /* generate in registers, 16-byte stores on peer pointers     */
+#define B200PROBE_A2A_PUSH_BUF    3   /* bulk-load the local send chunk, bulk-store into the peer   */
 
 typedef struct b200probe_a2a_cfg {
-    uint64_t bytes_per_pair;        /* S; 0 = 256 MiB                                              */
+    uint64_t bytes_per_pair;        /* S, multiple of 16; 0 = 256 MiB                              */
     int      mode;
     int      warmup, reps;          /* 0,0 = 2,10                                                  */
     uint32_t seed;
     int      verify;
-    int      ctas_per_peer;         /* 0 = default                                                 */
-    int      variant;               /* B200PROBE_VARIANT_TMA (bulk stores to the peer) or _DIRECT   */
+    int      ctas_per_peer;         /* 0 = default (about one CTA per SM in total)                 */
+    int      variant;               /* B200PROBE_A2A_PULL_TMA ...                                  */
 } b200probe_a2a_cfg_t;
 
 typedef struct b200probe_a2a_result {
     int      g;
-    double   ms_median, ms_best;    /* of the all-pairs exchange (modes 0, 2)                       */
+    double   ms_median, ms_best;    /* of the all-pairs exchange (modes 0, 2), max over devices     */
     double   egress_gbs[B200PROBE_MAX_DEVICES];   /* (G-1)*S / t per GPU, payload bytes            */
     double   ingress_gbs[B200PROBE_MAX_DEVICES];
     double   min_pair_gbs, max_pair_gbs;
-    int      verified;
+    int      verified;              /* 1 = every landed chunk equals the regenerated pattern        */
 } b200probe_a2a_result_t;
 
 /* Single process, all GPUs (how the plugin daemon runs).  cuda_ordinals[g]; pair_gbs is g*g
@@ -202,24 +208,24 @@ int b200probe_nvlink_a2a(const int* cuda_ordinals, int g, const b200probe_a2a_cf
 /* Enable peer access between every ordered pair of the listed devices (idempotent). */
 int b200probe_enable_peer_access(const int* cuda_ordinals, int g);
 
-/* One process per GPU (bench under torchrun): each rank allocates its receive window, exports a
- * 64-byte IPC handle, the host exchanges handles (any transport), imports the peers' windows and
- * pushes its chunks into them.  window layout on every rank: [world][S] bytes, slot r = data
- * FROM rank r. */
+/* Building blocks (one process per GPU under torchrun, or a host that owns its windows).
+ * Window layout on every rank:  [recv: world x S][send: world x S]  bytes;
+ *   send[p] = this rank's chunk for rank p, recv[p] = where rank p's chunk lands.
+ * create -> (export the 64-byte IPC handle, exchange by any transport, import the peers') ->
+ * fill -> exchange.  */
 #define B200PROBE_IPC_HANDLE_BYTES 64
 int b200probe_a2a_window_create(int cuda_ordinal, int world, uint64_t bytes_per_pair,
                                 void** window, unsigned char* ipc_handle_out);
+int b200probe_a2a_window_fill(int cuda_ordinal, void* window, int rank, int world,
+                              uint64_t bytes_per_pair, uint32_t seed, void* stream);
 int b200probe_a2a_window_import(int cuda_ordinal, const unsigned char* ipc_handle, void** peer_window);
 int b200probe_a2a_window_release(int cuda_ordinal, void* window, int imported);
-/* Push: for every peer p != rank, fill slot `rank` of peer_windows[p] with pattern(rank,p,seed),
- * generated in registers and stored over NVLink; slot `rank` of the local window gets the local
- * chunk.  Asynchronous on `stream`. */
-int b200probe_a2a_push(int cuda_ordinal, int rank, int world, void* const* peer_windows,
-                       uint64_t bytes_per_pair, uint32_t seed, int ctas_per_peer, int variant, void* stream);
-/* Push from a resident send buffer [world][S] (copy over NVLink instead of generate). */
-int b200probe_a2a_push_buf(int cuda_ordinal, int rank, int world, const void* sendbuf,
-                           void* const* peer_windows, uint64_t bytes_per_pair,
-                           int ctas_per_peer, int variant, void* stream);
+/* One exchange step of `rank`, asynchronous on `stream`.  windows[r] = base of rank r's window as
+ * mapped in THIS process (windows[rank] is the local one).  only_peer: >= 0 that peer only;
+ * -1 every slot including the local one; -2 every peer, no local slot (pure NVLink traffic). */
+int b200probe_a2a_exchange(int cuda_ordinal, int rank, int world, void* const* windows,
+                           uint64_t bytes_per_pair, uint32_t seed, int variant, int ctas_per_peer,
+                           int only_peer, void* stream);
 /* Seed of the chunk rank `src` sends to rank `dst`. */
 uint32_t b200probe_a2a_chunk_seed(uint32_t seed, int src, int dst);
 

@@ -17,6 +17,7 @@ IPC_HANDLE_BYTES = 64
 HBM_READ, HBM_WRITE, HBM_COPY = 1, 2, 4
 VARIANT_TMA, VARIANT_DIRECT = 0, 1
 A2A_PEER_ALL, A2A_PEER_PAIR, A2A_NCCL = 0, 1, 2
+A2A_PULL_TMA, A2A_PUSH_TMA, A2A_PUSH_DIRECT, A2A_PUSH_BUF = 0, 1, 2, 3
 NVML_ERROR_TIMEOUT = 10
 EVENT_XID_CRITICAL = 0x8
 EVENT_DBE = 0x2
@@ -174,8 +175,8 @@ SIGNATURES = {
     "b200probe_a2a_window_create": (C.c_int, [C.c_int, C.c_int, C.c_uint64, _P(_vp), C.c_char_p]),
     "b200probe_a2a_window_import": (C.c_int, [C.c_int, C.c_char_p, _P(_vp)]),
     "b200probe_a2a_window_release": (C.c_int, [C.c_int, _vp, C.c_int]),
-    "b200probe_a2a_push": (C.c_int, [C.c_int, C.c_int, C.c_int, _P(_vp), C.c_uint64, C.c_uint32, C.c_int, C.c_int, _vp]),
-    "b200probe_a2a_push_buf": (C.c_int, [C.c_int, C.c_int, C.c_int, _vp, _P(_vp), C.c_uint64, C.c_int, C.c_int, _vp]),
+    "b200probe_a2a_window_fill": (C.c_int, [C.c_int, _vp, C.c_int, C.c_int, C.c_uint64, C.c_uint32, _vp]),
+    "b200probe_a2a_exchange": (C.c_int, [C.c_int, C.c_int, C.c_int, _P(_vp), C.c_uint64, C.c_uint32, C.c_int, C.c_int, C.c_int, _vp]),
     "b200probe_a2a_chunk_seed": (C.c_uint32, [C.c_uint32, C.c_int, C.c_int]),
     "b200probe_gemm": (C.c_int, [C.c_int, _P(GemmCfg), _P(GemmResult)]),
     "b200probe_gemm_launch": (C.c_int, [C.c_int, _vp, _vp, _vp, C.c_int, C.c_int, C.c_int, _vp]),

@@ -23,6 +23,11 @@ struct DevProps {
 };
 int device_props(int ordinal, DevProps* out);
 
+// Device-side check of a buffer against the closed-form pattern (hbm_sweep.cu): checksum + count of
+// words that differ.  d_partials = 4 x u64 scratch on the device; synchronises `stream`.
+struct VerifyResult { uint64_t sum; uint32_t x; uint64_t bad, first; };
+int verify_pattern(int ordinal, const void* buf, uint64_t bytes, uint32_t seed, unsigned long long* d_partials, void* stream, VerifyResult* out);
+
 inline int cuda_rc(int cuda_err) { return cuda_err == 0 ? 0 : B200PROBE_CUDA_BASE + cuda_err; }
 
 }  // namespace b200

@@ -436,6 +436,27 @@ int verify_pass(int ordinal, const uint8_t* buf, uint64_t bytes, uint32_t seed, 
 
 }  // namespace
 
+namespace b200 {
+int verify_pattern(int ordinal, const void* buf, uint64_t bytes, uint32_t seed, unsigned long long* d_partials, void* stream, VerifyResult* out) {
+    DevProps props;
+    int rc = device_props(ordinal, &props);
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    static const unsigned long long init[4] = {0, 0, 0, ~0ull};
+    B200_CUDA_TRY(cudaSetDevice(ordinal));
+    B200_CUDA_TRY(cudaMemcpyAsync(d_partials, init, 32, cudaMemcpyHostToDevice, st));
+    if (bytes) {
+        hbm_verify_kernel<<<props.sms * 4, 512, 0, st>>>((const uint8_t*)buf, bytes, seed, d_partials);
+        B200_CUDA_TRY(cudaGetLastError());
+    }
+    unsigned long long h[4];
+    B200_CUDA_TRY(cudaMemcpyAsync(h, d_partials, 32, cudaMemcpyDeviceToHost, st));
+    B200_CUDA_TRY(cudaStreamSynchronize(st));
+    out->sum = h[0]; out->x = (uint32_t)h[1]; out->bad = h[2]; out->first = h[3];
+    return 0;
+}
+}  // namespace b200
+
 extern "C" {
 
 int b200probe_hbm_fill(int ordinal, void* dst, uint64_t bytes, uint32_t seed, const b200probe_hbm_cfg_t* cfg, void* stream) {

@@ -1,10 +1,19 @@
 // NVLink 5 all-to-all probe (no reference counterpart).
 //
-// Peer-memory kernels: every GPU pushes its (G-1) chunks straight into its peers' receive windows
-// with 16-byte stores on peer-mapped pointers (NVSwitch routes them; no staging copy, no NCCL).
-// The payload is either generated in registers (pure egress test: no local HBM read competes
-// with the links) or read from a resident send buffer.  NCCL grouped send/recv is kept beside it
-// as the library leg for contrast (dlopen'ed; mode B200PROBE_A2A_NCCL).
+// Every rank owns one window in HBM:  [recv: world x S bytes][send: world x S bytes]
+//   send[p] = the chunk this rank has for rank p   (pattern under chunk_seed(seed, rank, p))
+//   recv[p] = where rank p's chunk for this rank lands
+// Windows are peer-mapped (cudaDeviceEnablePeerAccess in one process, cudaIpc* across processes)
+// and the exchange is done by OUR kernels over those mappings — no NCCL on the data path:
+//   PULL_TMA    (default) each rank bulk-LOADS its peers' send chunks over NVLink into shared
+//               memory (cp.async.bulk, SASS UBLKCP) and bulk-stores them into its own recv slots.
+//               Reads move 781 GB/s per direction on B200; writes only 712 (profiles/p2p_pull_tune_r01.txt)
+//   PUSH_TMA    pattern generated into shared memory, bulk-STORED into the peers' recv slots
+//   PUSH_DIRECT pattern generated in registers, 16-byte stores on the peer pointers
+//   PUSH_BUF    local send chunk bulk-loaded, bulk-stored to the peer
+// CTAs are partitioned per peer so every peer's traffic is in flight at once (NVSwitch gives each
+// GPU its full port bandwidth to any mix of peers).  NCCL grouped send/recv is kept as the library
+// leg for contrast (mode B200PROBE_A2A_NCCL, dlopen'ed).
 //
 // Roofline: NVLink bound.  Algorithmic bytes per GPU per direction: (G-1)*S payload bytes.
 #include <cuda_runtime.h>
@@ -19,64 +28,37 @@
 namespace {
 
 constexpr int kMaxWorld = 16;
+constexpr int kRingWarps = 4, kRingMaxStages = 8;
 
 struct PeerTable {
-    uint8_t* win[kMaxWorld];   // base of every rank's receive window, peer-mapped (win[rank] is local)
+    uint8_t* win[kMaxWorld];   // base of every rank's window (win[rank] is local)
 };
 
 B200_HD uint32_t chunk_seed(uint32_t seed, int src, int dst) { return seed ^ b200_mix32((uint32_t)(src * 251 + dst * 7 + 1)); }
 
-// grid.x = world * ctas_per_peer; CTA b serves destination b / ctas_per_peer.
-// only_dst >= 0 restricts the push to one destination (pairwise-isolated pass); -1 = all slots
-// including the local one; -2 = all peers but not the local slot (pure NVLink traffic).
-template <bool FROM_BUF>
-__global__ void __launch_bounds__(512) a2a_push_kernel(PeerTable peers, const uint8_t* __restrict__ sendbuf, int rank, int world,
-                                                       uint64_t S, uint32_t seed, int ctas_per_peer, int only_dst) {
-    const int dst = blockIdx.x / ctas_per_peer;
-    if (dst >= world) return;
-    if (only_dst >= 0 && dst != only_dst) return;
-    if (only_dst == -2 && dst == rank) return;      // -2: every peer, skip the local slot
-    const int sub = blockIdx.x % ctas_per_peer;
-    uint4* __restrict__ out = reinterpret_cast<uint4*>(peers.win[dst] + (uint64_t)rank * S);
-    const uint4* __restrict__ in = reinterpret_cast<const uint4*>(sendbuf + (uint64_t)dst * S);
-    const uint32_t cs = chunk_seed(seed, rank, dst);
-    const uint64_t nvec = S >> 4;
-    const uint64_t stride = (uint64_t)ctas_per_peer * blockDim.x;
-    uint64_t i = (uint64_t)sub * blockDim.x + threadIdx.x;
-    constexpr int U = 8;
-    for (; i + (U - 1) * stride < nvec; i += U * stride) {
-        uint4 v[U];
-#pragma unroll
-        for (int j = 0; j < U; ++j) {
-            if (FROM_BUF) v[j] = __ldcs(in + i + j * stride);
-            else {
-                uint64_t w = (i + j * stride) * 4;
-                v[j] = make_uint4(b200_pattern_word(w, cs), b200_pattern_word(w + 1, cs), b200_pattern_word(w + 2, cs), b200_pattern_word(w + 3, cs));
-            }
-        }
-#pragma unroll
-        for (int j = 0; j < U; ++j) out[i + j * stride] = v[j];
-    }
-    for (; i < nvec; i += stride) {
-        uint4 v;
-        if (FROM_BUF) v = __ldcs(in + i);
-        else {
-            uint64_t w = i * 4;
-            v = make_uint4(b200_pattern_word(w, cs), b200_pattern_word(w + 1, cs), b200_pattern_word(w + 2, cs), b200_pattern_word(w + 3, cs));
-        }
-        out[i] = v;
-    }
+struct XArgs {
+    PeerTable peers;
+    int rank, world;
+    uint64_t S;
+    uint32_t seed;
+    int ctas_per_peer;
+    int only_peer;     // >=0 one peer; -1 all slots incl. the local one; -2 all peers, no local slot
+    int variant;
+    uint32_t SB, NS;   // ring stage bytes / stages
+};
+
+__device__ __forceinline__ bool cta_peer(const XArgs& a, int* peer, int* sub) {
+    const int p = blockIdx.x / a.ctas_per_peer;
+    if (p >= a.world) return false;
+    if (a.only_peer >= 0 && p != a.only_peer) return false;
+    if (a.only_peer == -2 && p == a.rank) return false;
+    *peer = p;
+    *sub = blockIdx.x % a.ctas_per_peer;
+    return true;
 }
 
-
-// TMA variant: each warp owns a ring of shared-memory stages, generates (or bulk-loads) a chunk
-// into a stage and bulk-stores it (cp.async.bulk shared->global, SASS UBLKCP) to the PEER window:
-// the copy engine of the SM streams whole 8-32 KiB bursts into NVLink instead of 16-byte stores.
-constexpr int kRingWarps = 4, kRingMaxStages = 8;
-template <bool FROM_BUF>
-__global__ void __launch_bounds__(kRingWarps * 32) a2a_ring_push_kernel(PeerTable peers, const uint8_t* __restrict__ sendbuf, int rank, int world,
-                                                                         uint64_t S, uint32_t seed, int ctas_per_peer, int only_dst,
-                                                                         uint32_t SB, uint32_t NS) {
+// ---- TMA ring exchange: one ring of shared-memory stages per warp ---------------------------------
+__global__ void __launch_bounds__(kRingWarps * 32) a2a_ring_kernel(XArgs a) {
     using namespace b200ptx;
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ __align__(8) uint64_t full_bar[kRingWarps * kRingMaxStages];
@@ -86,16 +68,23 @@ __global__ void __launch_bounds__(kRingWarps * 32) a2a_ring_push_kernel(PeerTabl
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
-    const int dst = blockIdx.x / ctas_per_peer;
-    if (dst >= world) return;
-    if (only_dst >= 0 && dst != only_dst) return;
-    if (only_dst == -2 && dst == rank) return;
-    const int sub = blockIdx.x % ctas_per_peer;
-    uint8_t* out = peers.win[dst] + (uint64_t)rank * S;
-    const uint8_t* in = sendbuf + (uint64_t)dst * S;
-    const uint32_t cs = chunk_seed(seed, rank, dst);
+    int p, sub;
+    if (!cta_peer(a, &p, &sub)) return;
+    const uint64_t S = a.S;
+    const uint32_t SB = a.SB, NS = a.NS;
+    uint8_t* const me = a.peers.win[a.rank];
+    uint8_t* const them = a.peers.win[p];
+    const uint8_t* in;
+    uint8_t* out;
+    if (a.variant == B200PROBE_A2A_PULL_TMA) {          // their send[rank] -> my recv[p]
+        in = them + ((uint64_t)a.world + a.rank) * S;
+        out = me + (uint64_t)p * S;
+    } else {                                            // (my send[p] | generated) -> their recv[rank]
+        in = me + ((uint64_t)a.world + p) * S;
+        out = them + (uint64_t)a.rank * S;
+    }
     const uint64_t nchunks = (S + SB - 1) / SB;
-    const uint64_t worker = (uint64_t)sub * kRingWarps + warp, nworkers = (uint64_t)ctas_per_peer * kRingWarps;
+    const uint64_t worker = (uint64_t)sub * kRingWarps + warp, nworkers = (uint64_t)a.ctas_per_peer * kRingWarps;
     const uint64_t n_my = worker < nchunks ? (nchunks - worker + nworkers - 1) / nworkers : 0;
     const uint32_t ring = smem_u32(smem) + warp * NS * SB;
     uint8_t* ring_ptr = smem + (size_t)warp * NS * SB;
@@ -103,9 +92,9 @@ __global__ void __launch_bounds__(kRingWarps * 32) a2a_ring_push_kernel(PeerTabl
     const uint64_t pol = policy_evict_first();
     auto off_of = [&](uint64_t k) { return (worker + k * nworkers) * (uint64_t)SB; };
     auto len_of = [&](uint64_t k) { return (uint32_t)min((uint64_t)SB, S - off_of(k)); };
-    uint32_t cs_stage = 0, cph = 0;
-    if (FROM_BUF) {
-        if (lane == 0 && n_my > 0) {     // bulk-load local chunk, bulk-store to the peer; registers untouched
+    uint32_t cs = 0, cph = 0;
+    if (a.variant != B200PROBE_A2A_PUSH_TMA) {
+        if (lane == 0 && n_my > 0) {       // bulk load -> bulk store; the data never touches registers
             uint64_t issued = 0;
             uint32_t ps = 0;
             auto load_next = [&]() {
@@ -118,73 +107,100 @@ __global__ void __launch_bounds__(kRingWarps * 32) a2a_ring_push_kernel(PeerTabl
             const uint64_t ahead = min((uint64_t)(NS - 1), n_my);
             while (issued < ahead) load_next();
             for (uint64_t k = 0; k < n_my; ++k) {
-                mbar_wait(bar0 + cs_stage * 8, cph);
-                bulk_s2g(out + off_of(k), ring + cs_stage * SB, len_of(k), pol);
+                mbar_wait(bar0 + cs * 8, cph);
+                bulk_s2g(out + off_of(k), ring + cs * SB, len_of(k), pol);
                 bulk_commit();
                 if (issued < n_my) { bulk_wait_read<1>(); load_next(); }
-                if (++cs_stage == NS) { cs_stage = 0; cph ^= 1; }
+                if (++cs == NS) { cs = 0; cph ^= 1; }
             }
             bulk_wait_all();
         }
     } else {
+        const uint32_t sd = chunk_seed(a.seed, a.rank, p);
         for (uint64_t k = 0; k < n_my; ++k) {
             if (k >= NS) {
                 if (lane == 0) bulk_wait_read_dyn((int)NS - 1);
                 __syncwarp();
             }
-            uint4* st = reinterpret_cast<uint4*>(ring_ptr + (size_t)cs_stage * SB);
+            uint4* st = reinterpret_cast<uint4*>(ring_ptr + (size_t)cs * SB);
             const uint32_t nvec = len_of(k) >> 4;
             const uint64_t w0 = off_of(k) >> 2;
 #pragma unroll 4
             for (uint32_t i = lane; i < nvec; i += 32) {
                 const uint64_t w = w0 + (uint64_t)i * 4;
-                st[i] = make_uint4(b200_pattern_word(w, cs), b200_pattern_word(w + 1, cs), b200_pattern_word(w + 2, cs), b200_pattern_word(w + 3, cs));
+                st[i] = make_uint4(b200_pattern_word(w, sd), b200_pattern_word(w + 1, sd), b200_pattern_word(w + 2, sd), b200_pattern_word(w + 3, sd));
             }
             fence_proxy_async_smem();
             __syncwarp();
-            if (lane == 0) { bulk_s2g(out + off_of(k), ring + cs_stage * SB, len_of(k), pol); bulk_commit(); }
-            if (++cs_stage == NS) cs_stage = 0;
+            if (lane == 0) { bulk_s2g(out + off_of(k), ring + cs * SB, len_of(k), pol); bulk_commit(); }
+            if (++cs == NS) cs = 0;
         }
         if (lane == 0) bulk_wait_all();
     }
 }
 
-int default_ctas_per_peer(int sms, int world) { return std::max(1, (sms * 4 + world - 1) / world); }
+// ---- direct push: pattern in registers, 16-byte stores on the peer pointer --------------------------
+__global__ void __launch_bounds__(512) a2a_direct_kernel(XArgs a) {
+    int p, sub;
+    if (!cta_peer(a, &p, &sub)) return;
+    uint4* __restrict__ out = reinterpret_cast<uint4*>(a.peers.win[p] + (uint64_t)a.rank * a.S);
+    const uint32_t sd = chunk_seed(a.seed, a.rank, p);
+    const uint64_t nvec = a.S >> 4;
+    const uint64_t stride = (uint64_t)a.ctas_per_peer * blockDim.x;
+    uint64_t i = (uint64_t)sub * blockDim.x + threadIdx.x;
+    constexpr int U = 8;
+    for (; i + (U - 1) * stride < nvec; i += U * stride) {
+        uint4 v[U];
+#pragma unroll
+        for (int j = 0; j < U; ++j) {
+            const uint64_t w = (i + j * stride) * 4;
+            v[j] = make_uint4(b200_pattern_word(w, sd), b200_pattern_word(w + 1, sd), b200_pattern_word(w + 2, sd), b200_pattern_word(w + 3, sd));
+        }
+#pragma unroll
+        for (int j = 0; j < U; ++j) out[i + j * stride] = v[j];
+    }
+    for (; i < nvec; i += stride) {
+        const uint64_t w = i * 4;
+        out[i] = make_uint4(b200_pattern_word(w, sd), b200_pattern_word(w + 1, sd), b200_pattern_word(w + 2, sd), b200_pattern_word(w + 3, sd));
+    }
+}
 
-int launch_push(int ordinal, int rank, int world, void* const* windows, const void* sendbuf, uint64_t S, uint32_t seed, int ctas_per_peer,
-                int only_dst, int variant, cudaStream_t stream) {
+int launch_exchange(int ordinal, int rank, int world, void* const* windows, uint64_t S, uint32_t seed, int variant, int ctas_per_peer,
+                    int only_peer, cudaStream_t stream) {
     if (world < 1 || world > kMaxWorld || rank < 0 || rank >= world || !windows) { b200::set_error("a2a: bad rank/world"); return B200PROBE_EINVAL; }
     if (S & 15) { b200::set_error("a2a: bytes_per_pair must be a multiple of 16"); return B200PROBE_EINVAL; }
+    if (variant < 0 || variant > B200PROBE_A2A_PUSH_BUF) { b200::set_error("a2a: unknown variant %d", variant); return B200PROBE_EINVAL; }
+    if (only_peer >= world) { b200::set_error("a2a: peer %d out of range", only_peer); return B200PROBE_ERANGE; }
     b200::DevProps props;
     int rc = b200::device_props(ordinal, &props);
     if (rc) return rc;
     if (S == 0) return 0;
     B200_CUDA_TRY(cudaSetDevice(ordinal));
-    PeerTable t;
-    memset(&t, 0, sizeof(t));
-    for (int i = 0; i < world; ++i) t.win[i] = (uint8_t*)windows[i];
-    const int targets = only_dst >= 0 ? 1 : world;
-    if (variant == B200PROBE_VARIANT_TMA) {
-        // one CTA per SM in total, split over the destinations; 4 warps x 4 stages x 8 KiB per CTA
-        if (ctas_per_peer <= 0) ctas_per_peer = std::max(1, props.sms / targets);
-        const uint32_t SB = 8192, NS = 4;
-        const size_t smem = (size_t)kRingWarps * NS * SB;
-        static bool attr[2] = {false, false};
-        // per-device function attribute; cheap enough to set on every launch
-        if (sendbuf) B200_CUDA_TRY(cudaFuncSetAttribute(a2a_ring_push_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        else B200_CUDA_TRY(cudaFuncSetAttribute(a2a_ring_push_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        (void)attr;
-        dim3 g((unsigned)(world * ctas_per_peer));
-        if (sendbuf) a2a_ring_push_kernel<true><<<g, kRingWarps * 32, smem, stream>>>(t, (const uint8_t*)sendbuf, rank, world, S, seed, ctas_per_peer, only_dst, SB, NS);
-        else a2a_ring_push_kernel<false><<<g, kRingWarps * 32, smem, stream>>>(t, nullptr, rank, world, S, seed, ctas_per_peer, only_dst, SB, NS);
-        B200_CUDA_TRY(cudaGetLastError());
-        return 0;
+    XArgs a;
+    memset(&a, 0, sizeof(a));
+    for (int i = 0; i < world; ++i) a.peers.win[i] = (uint8_t*)windows[i];
+    a.rank = rank; a.world = world; a.S = S; a.seed = seed; a.only_peer = only_peer; a.variant = variant;
+    const int targets = only_peer >= 0 ? 1 : std::max(1, world - (only_peer == -2 ? 1 : 0));
+    if (variant == B200PROBE_A2A_PUSH_DIRECT) {
+        a.ctas_per_peer = ctas_per_peer > 0 ? ctas_per_peer : std::max(1, (props.sms * 4 + targets - 1) / targets);
+        a2a_direct_kernel<<<world * a.ctas_per_peer, 512, 0, stream>>>(a);
+    } else {
+        // about one CTA per SM in total, split over the peers; 4 warps x 4 stages x 8 KiB = 128 KiB per CTA
+        a.ctas_per_peer = ctas_per_peer > 0 ? ctas_per_peer : std::max(1, props.sms / targets);
+        a.SB = 8192; a.NS = 4;
+        const size_t smem = (size_t)kRingWarps * a.NS * a.SB;
+        B200_CUDA_TRY(cudaFuncSetAttribute(a2a_ring_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        a2a_ring_kernel<<<world * a.ctas_per_peer, kRingWarps * 32, smem, stream>>>(a);
     }
-    if (ctas_per_peer <= 0) ctas_per_peer = default_ctas_per_peer(props.sms, targets);
-    dim3 grid((unsigned)(world * ctas_per_peer));
-    if (sendbuf) a2a_push_kernel<true><<<grid, 512, 0, stream>>>(t, (const uint8_t*)sendbuf, rank, world, S, seed, ctas_per_peer, only_dst);
-    else a2a_push_kernel<false><<<grid, 512, 0, stream>>>(t, nullptr, rank, world, S, seed, ctas_per_peer, only_dst);
     B200_CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+int fill_send_half(int ordinal, void* window, int rank, int world, uint64_t S, uint32_t seed, cudaStream_t stream) {
+    for (int p = 0; p < world; ++p) {
+        int rc = b200probe_hbm_fill(ordinal, (uint8_t*)window + ((uint64_t)world + p) * S, S, chunk_seed(seed, rank, p), nullptr, stream);
+        if (rc) return rc;
+    }
     return 0;
 }
 
@@ -218,7 +234,7 @@ int load_nccl(Nccl* n) {
 
 struct PerDev {
     int ordinal = -1;
-    uint8_t *window = nullptr, *sendbuf = nullptr;
+    uint8_t* window = nullptr;
     unsigned long long* partials = nullptr;
     cudaStream_t stream = nullptr;
     cudaEvent_t e0 = nullptr, e1 = nullptr;
@@ -234,7 +250,6 @@ struct A2aCtx {
             if (p.ordinal < 0) continue;
             cudaSetDevice(p.ordinal);
             if (p.window) cudaFree(p.window);
-            if (p.sendbuf) cudaFree(p.sendbuf);
             if (p.partials) cudaFree(p.partials);
             if (p.e0) cudaEventDestroy(p.e0);
             if (p.e1) cudaEventDestroy(p.e1);
@@ -280,14 +295,15 @@ int b200probe_enable_peer_access(const int* ordinals, int g) {
 }
 
 int b200probe_a2a_window_create(int ordinal, int world, uint64_t S, void** window, unsigned char* handle_out) {
-    if (!window || world < 1 || world > kMaxWorld) return B200PROBE_EINVAL;
+    if (!window || world < 1 || world > kMaxWorld || (S & 15)) return B200PROBE_EINVAL;
     b200::DevProps props;
     int rc = b200::device_props(ordinal, &props);
     if (rc) return rc;
     B200_CUDA_TRY(cudaSetDevice(ordinal));
     void* p = nullptr;
-    B200_CUDA_TRY(cudaMalloc(&p, std::max<uint64_t>(16, (uint64_t)world * S)));
-    B200_CUDA_TRY(cudaMemset(p, 0, std::max<uint64_t>(16, (uint64_t)world * S)));
+    const uint64_t bytes = std::max<uint64_t>(16, 2ull * world * S);
+    B200_CUDA_TRY(cudaMalloc(&p, bytes));
+    B200_CUDA_TRY(cudaMemset(p, 0, bytes));
     if (handle_out) {
         static_assert(sizeof(cudaIpcMemHandle_t) == B200PROBE_IPC_HANDLE_BYTES, "IPC handle size");
         cudaIpcMemHandle_t h;
@@ -297,6 +313,11 @@ int b200probe_a2a_window_create(int ordinal, int world, uint64_t S, void** windo
     }
     *window = p;
     return 0;
+}
+
+int b200probe_a2a_window_fill(int ordinal, void* window, int rank, int world, uint64_t S, uint32_t seed, void* stream) {
+    if (!window || world < 1 || world > kMaxWorld || rank < 0 || rank >= world || (S & 15)) return B200PROBE_EINVAL;
+    return fill_send_half(ordinal, window, rank, world, S, seed, (cudaStream_t)stream);
 }
 
 int b200probe_a2a_window_import(int ordinal, const unsigned char* handle, void** peer_window) {
@@ -321,15 +342,9 @@ int b200probe_a2a_window_release(int ordinal, void* window, int imported) {
     return 0;
 }
 
-int b200probe_a2a_push(int ordinal, int rank, int world, void* const* windows, uint64_t S, uint32_t seed, int ctas_per_peer, int variant,
-                       void* stream) {
-    return launch_push(ordinal, rank, world, windows, nullptr, S, seed, ctas_per_peer, -1, variant, (cudaStream_t)stream);
-}
-
-int b200probe_a2a_push_buf(int ordinal, int rank, int world, const void* sendbuf, void* const* windows, uint64_t S, int ctas_per_peer,
-                           int variant, void* stream) {
-    if (!sendbuf) return B200PROBE_EINVAL;
-    return launch_push(ordinal, rank, world, windows, sendbuf, S, 0, ctas_per_peer, -1, variant, (cudaStream_t)stream);
+int b200probe_a2a_exchange(int ordinal, int rank, int world, void* const* windows, uint64_t S, uint32_t seed, int variant, int ctas_per_peer,
+                           int only_peer, void* stream) {
+    return launch_exchange(ordinal, rank, world, windows, S, seed, variant, ctas_per_peer, only_peer, (cudaStream_t)stream);
 }
 
 int b200probe_nvlink_a2a(const int* ordinals, int g, const b200probe_a2a_cfg_t* cfg_in, double* pair_gbs, b200probe_a2a_result_t* out) {
@@ -342,51 +357,40 @@ int b200probe_nvlink_a2a(const int* ordinals, int g, const b200probe_a2a_cfg_t* 
     if (cfg.reps < 1) cfg.reps = 1;
     if (!cfg.seed) cfg.seed = 0xB200u;
     const uint64_t S = cfg.bytes_per_pair;
+    if (S & 15) { b200::set_error("a2a: bytes_per_pair must be a multiple of 16"); return B200PROBE_EINVAL; }
     memset(out, 0, sizeof(*out));
     out->g = g;
     out->verified = -1;
     if (pair_gbs) std::fill(pair_gbs, pair_gbs + g * g, 0.0);
+    const bool nccl_mode = cfg.mode == B200PROBE_A2A_NCCL;
+    const bool pull = !nccl_mode && cfg.variant == B200PROBE_A2A_PULL_TMA;
 
-    {
-        int rc = b200probe_enable_peer_access(ordinals, g);
-        if (rc) return rc;
-    }
+    int rc = b200probe_enable_peer_access(ordinals, g);
+    if (rc) return rc;
     A2aCtx ctx;
     ctx.d.resize(g);
-    // peer access, windows
     for (int i = 0; i < g; ++i) {
-        b200::DevProps props;
-        int rc = b200::device_props(ordinals[i], &props);
-        if (rc) return rc;
         B200_CUDA_TRY(cudaSetDevice(ordinals[i]));
         PerDev& p = ctx.d[i];
         p.ordinal = ordinals[i];
         B200_CUDA_TRY(cudaStreamCreateWithFlags(&p.stream, cudaStreamNonBlocking));
         B200_CUDA_TRY(cudaEventCreate(&p.e0));
         B200_CUDA_TRY(cudaEventCreate(&p.e1));
-        B200_CUDA_TRY(cudaMalloc(&p.window, (size_t)g * S));
-        B200_CUDA_TRY(cudaMemset(p.window, 0, (size_t)g * S));
-        B200_CUDA_TRY(cudaMalloc(&p.partials, 16));
+        B200_CUDA_TRY(cudaMalloc(&p.window, 2ull * g * S));
+        B200_CUDA_TRY(cudaMemsetAsync(p.window, 0, (size_t)g * S, p.stream));
+        B200_CUDA_TRY(cudaMalloc(&p.partials, 32));
+        rc = fill_send_half(p.ordinal, p.window, i, g, S, cfg.seed, p.stream);
+        if (rc) return rc;
+        B200_CUDA_TRY(cudaStreamSynchronize(p.stream));
     }
     void* windows[kMaxWorld] = {nullptr};
     for (int i = 0; i < g; ++i) windows[i] = ctx.d[i].window;
 
-    const bool nccl_mode = cfg.mode == B200PROBE_A2A_NCCL;
     if (nccl_mode) {
-        int rc = load_nccl(&ctx.nccl);
+        rc = load_nccl(&ctx.nccl);
         if (rc) return rc;
         ctx.comms.assign(g, nullptr);
         NCCL_TRY(ctx.nccl, ctx.nccl.CommInitAll(ctx.comms.data(), g, ordinals));
-        for (int i = 0; i < g; ++i) {   // resident send buffers: chunk for peer p at [p][S]
-            PerDev& p = ctx.d[i];
-            B200_CUDA_TRY(cudaSetDevice(p.ordinal));
-            B200_CUDA_TRY(cudaMalloc(&p.sendbuf, (size_t)g * S));
-            for (int j = 0; j < g; ++j) {
-                int rc2 = b200probe_hbm_fill(p.ordinal, p.sendbuf + (size_t)j * S, S, chunk_seed(cfg.seed, i, j), nullptr, p.stream);
-                if (rc2) return rc2;
-            }
-            B200_CUDA_TRY(cudaStreamSynchronize(p.stream));
-        }
     }
 
     auto sync_all = [&]() -> int {
@@ -398,16 +402,22 @@ int b200probe_nvlink_a2a(const int* ordinals, int g, const b200probe_a2a_cfg_t* 
     };
     // one all-pairs exchange; per-device elapsed ms into t[]
     auto exchange = [&](bool timed, std::vector<double>* t) -> int {
-        if (nccl_mode) {
-            for (int i = 0; i < g; ++i) {
-                B200_CUDA_TRY(cudaSetDevice(ctx.d[i].ordinal));
-                if (timed) B200_CUDA_TRY(cudaEventRecord(ctx.d[i].e0, ctx.d[i].stream));
+        for (int i = 0; i < g; ++i) {
+            B200_CUDA_TRY(cudaSetDevice(ctx.d[i].ordinal));
+            if (timed) B200_CUDA_TRY(cudaEventRecord(ctx.d[i].e0, ctx.d[i].stream));
+            if (!nccl_mode) {
+                // -2: the local slot is HBM traffic, not NVLink: kept out of the timed exchange
+                int r2 = launch_exchange(ctx.d[i].ordinal, i, g, windows, S, cfg.seed, cfg.variant, cfg.ctas_per_peer, -2, ctx.d[i].stream);
+                if (r2) return r2;
+                if (timed) B200_CUDA_TRY(cudaEventRecord(ctx.d[i].e1, ctx.d[i].stream));
             }
+        }
+        if (nccl_mode) {
             NCCL_TRY(ctx.nccl, ctx.nccl.GroupStart());
             for (int i = 0; i < g; ++i)
                 for (int j = 0; j < g; ++j) {
                     if (i == j) continue;
-                    NCCL_TRY(ctx.nccl, ctx.nccl.Send(ctx.d[i].sendbuf + (size_t)j * S, S, /*ncclUint8*/ 1, j, ctx.comms[i], ctx.d[i].stream));
+                    NCCL_TRY(ctx.nccl, ctx.nccl.Send(ctx.d[i].window + ((size_t)g + j) * S, S, /*ncclUint8*/ 1, j, ctx.comms[i], ctx.d[i].stream));
                     NCCL_TRY(ctx.nccl, ctx.nccl.Recv(ctx.d[i].window + (size_t)j * S, S, 1, j, ctx.comms[i], ctx.d[i].stream));
                 }
             NCCL_TRY(ctx.nccl, ctx.nccl.GroupEnd());
@@ -415,19 +425,9 @@ int b200probe_nvlink_a2a(const int* ordinals, int g, const b200probe_a2a_cfg_t* 
                 B200_CUDA_TRY(cudaSetDevice(ctx.d[i].ordinal));
                 if (timed) B200_CUDA_TRY(cudaEventRecord(ctx.d[i].e1, ctx.d[i].stream));
             }
-        } else {
-            for (int i = 0; i < g; ++i) {
-                PerDev& p = ctx.d[i];
-                B200_CUDA_TRY(cudaSetDevice(p.ordinal));
-                if (timed) B200_CUDA_TRY(cudaEventRecord(p.e0, p.stream));
-                // -2: skip the local slot in the timed exchange (it is HBM traffic, not NVLink)
-                int rc = launch_push(p.ordinal, i, g, windows, nullptr, S, cfg.seed, cfg.ctas_per_peer, -2, cfg.variant, p.stream);
-                if (rc) return rc;
-                if (timed) B200_CUDA_TRY(cudaEventRecord(p.e1, p.stream));
-            }
         }
-        int rc = sync_all();
-        if (rc) return rc;
+        int r3 = sync_all();
+        if (r3) return r3;
         if (timed && t) {
             t->assign(g, 0.0);
             for (int i = 0; i < g; ++i) {
@@ -439,18 +439,26 @@ int b200probe_nvlink_a2a(const int* ordinals, int g, const b200probe_a2a_cfg_t* 
         }
         return 0;
     };
+    auto local_slots = [&]() -> int {       // own chunk into own recv slot (not NVLink traffic; completes the window)
+        for (int i = 0; i < g; ++i) {
+            B200_CUDA_TRY(cudaSetDevice(ctx.d[i].ordinal));
+            B200_CUDA_TRY(cudaMemcpyAsync(ctx.d[i].window + (size_t)i * S, ctx.d[i].window + ((size_t)g + i) * S, S, cudaMemcpyDeviceToDevice, ctx.d[i].stream));
+        }
+        return sync_all();
+    };
 
     if (cfg.mode == B200PROBE_A2A_PEER_PAIR) {
         double mn = 1e300, mx = 0;
-        for (int i = 0; i < g; ++i)
-            for (int j = 0; j < g; ++j) {
-                if (i == j) continue;
-                PerDev& p = ctx.d[i];
+        for (int src = 0; src < g; ++src)
+            for (int dst = 0; dst < g; ++dst) {
+                if (src == dst) continue;
+                const int runner = pull ? dst : src, peer = pull ? src : dst;    // the rank whose kernel moves src -> dst
+                PerDev& p = ctx.d[runner];
                 B200_CUDA_TRY(cudaSetDevice(p.ordinal));
                 std::vector<double> ts;
                 for (int it = -cfg.warmup; it < cfg.reps; ++it) {
                     if (it >= 0) B200_CUDA_TRY(cudaEventRecord(p.e0, p.stream));
-                    int rc = launch_push(p.ordinal, i, g, windows, nullptr, S, cfg.seed, cfg.ctas_per_peer, j, cfg.variant, p.stream);
+                    rc = launch_exchange(p.ordinal, runner, g, windows, S, cfg.seed, cfg.variant, cfg.ctas_per_peer, peer, p.stream);
                     if (rc) return rc;
                     if (it >= 0) {
                         float ms;
@@ -461,24 +469,17 @@ int b200probe_nvlink_a2a(const int* ordinals, int g, const b200probe_a2a_cfg_t* 
                     }
                 }
                 B200_CUDA_TRY(cudaStreamSynchronize(p.stream));
-                double gbs = (double)S / (median_of(ts) * 1e-3) / 1e9;
-                if (pair_gbs) pair_gbs[i * g + j] = gbs;
+                const double gbs = (double)S / (median_of(ts) * 1e-3) / 1e9;
+                if (pair_gbs) pair_gbs[src * g + dst] = gbs;
                 mn = std::min(mn, gbs); mx = std::max(mx, gbs);
             }
         out->min_pair_gbs = mn; out->max_pair_gbs = mx;
-        // the local slots are not written in pair mode; fill them so verification covers the window
-        for (int i = 0; i < g; ++i) {
-            int rc = launch_push(ctx.d[i].ordinal, i, g, windows, nullptr, S, cfg.seed, cfg.ctas_per_peer, i, cfg.variant, ctx.d[i].stream);
-            if (rc) return rc;
-        }
-        int rc = sync_all();
-        if (rc) return rc;
     } else {
         std::vector<std::vector<double>> per_dev(g);
         std::vector<double> wall;
         for (int it = -cfg.warmup; it < cfg.reps; ++it) {
             std::vector<double> t;
-            int rc = exchange(it >= 0, &t);
+            rc = exchange(it >= 0, &t);
             if (rc) return rc;
             if (it >= 0) {
                 for (int i = 0; i < g; ++i) per_dev[i].push_back(t[i]);
@@ -490,47 +491,35 @@ int b200probe_nvlink_a2a(const int* ordinals, int g, const b200probe_a2a_cfg_t* 
         const double payload = (double)(g - 1) * (double)S;
         double mn = 1e300, mx = 0;
         for (int i = 0; i < g; ++i) {
-            double ti = median_of(per_dev[i]);
-            out->egress_gbs[i] = payload / (ti * 1e-3) / 1e9;
-            out->ingress_gbs[i] = payload / (out->ms_median * 1e-3) / 1e9;   // bytes landed over the common window
+            const double own = payload / (median_of(per_dev[i]) * 1e-3) / 1e9;      // the direction rank i's kernel drives
+            const double common = payload / (out->ms_median * 1e-3) / 1e9;          // the other direction, over the common window
+            out->egress_gbs[i] = pull ? common : own;
+            out->ingress_gbs[i] = pull ? own : common;
             for (int j = 0; j < g; ++j) {
                 if (i == j) continue;
-                double gbs = (double)S / (ti * 1e-3) / 1e9;                  // per-pair share under full concurrency
-                if (pair_gbs) pair_gbs[i * g + j] = gbs;
+                const double gbs = own / (g - 1);                                   // per-pair share under full concurrency
+                if (pair_gbs) pair_gbs[pull ? j * g + i : i * g + j] = gbs;
                 mn = std::min(mn, gbs); mx = std::max(mx, gbs);
             }
         }
         out->min_pair_gbs = mn; out->max_pair_gbs = mx;
-        if (!nccl_mode) {   // local slots (not part of the timed exchange)
-            for (int i = 0; i < g; ++i) {
-                int rc = launch_push(ctx.d[i].ordinal, i, g, windows, nullptr, S, cfg.seed, cfg.ctas_per_peer, i, cfg.variant, ctx.d[i].stream);
-                if (rc) return rc;
-            }
-            int rc = sync_all();
-            if (rc) return rc;
-        }
     }
+    rc = local_slots();
+    if (rc) return rc;
 
     if (cfg.verify) {
-        // expected checksum per (src,dst) chunk, closed form on the host
+        // every chunk that landed must equal the regenerated pattern under its (src,dst) seed
         int ok = 1;
         for (int dst = 0; dst < g && ok; ++dst) {
             PerDev& p = ctx.d[dst];
             B200_CUDA_TRY(cudaSetDevice(p.ordinal));
             for (int src = 0; src < g; ++src) {
-                if (nccl_mode && src == dst) continue;
-                B200_CUDA_TRY(cudaMemsetAsync(p.partials, 0, 16, p.stream));
-                int rc = b200probe_hbm_read(p.ordinal, p.window + (size_t)src * S, S, (uint64_t*)p.partials, nullptr, p.stream);
+                b200::VerifyResult v;
+                rc = b200::verify_pattern(p.ordinal, p.window + (size_t)src * S, S, chunk_seed(cfg.seed, src, dst), p.partials, p.stream, &v);
                 if (rc) return rc;
-                unsigned long long h[2];
-                B200_CUDA_TRY(cudaMemcpyAsync(h, p.partials, 16, cudaMemcpyDeviceToHost, p.stream));
-                B200_CUDA_TRY(cudaStreamSynchronize(p.stream));
-                const uint32_t cs = chunk_seed(cfg.seed, src, dst);
-                uint64_t es = 0; uint32_t ex = 0;
-                for (uint64_t w = 0; w < (S >> 2); ++w) { uint32_t v = b200_pattern_word(w, cs); es += v; ex ^= v; }
-                if (h[0] != es || (uint32_t)h[1] != ex) {
-                    b200::set_error("a2a: chunk %d->%d landed with checksum %llx/%x, expected %llx/%x", src, dst, h[0], (unsigned)h[1],
-                                    (unsigned long long)es, ex);
+                if (v.bad) {
+                    b200::set_error("a2a: chunk %d->%d landed with %llu wrong words (first at word %llu)", src, dst, (unsigned long long)v.bad,
+                                    (unsigned long long)v.first);
                     ok = 0;
                     break;
                 }

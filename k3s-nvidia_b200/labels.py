@@ -35,6 +35,7 @@ HBM_NOMINAL_GBS = 8000.0         # north_star's denominator
 HBM_MEASURED_GBS = 6565.8        # MEASURED_PEAKS.json hbm_gbs (torch copy_, read+write bytes)
 NVLINK_NOMINAL_GBS = 900.0       # per direction per GPU
 NVLINK_MEASURED_GBS = 770.0      # /opt/skills/guides/B200_PROFILING.md: peer copy per direction
+NVLINK_HEALTHY_GBS = 692.0       # this repo's push kernel with all 18 links up (profiles/a2a_tune_r01_2gpu.txt, +-0.3%)
 GEMM_NOMINAL_TFLOPS = 2250.0
 GEMM_MEASURED_TFLOPS = 1670.2
 
@@ -52,7 +53,8 @@ def _env_float(name: str, default: float) -> float:
 @dataclass
 class Thresholds:
     hbm_min_gbs: float = field(default_factory=lambda: _env_float("B200PROBE_HBM_MIN_GBS", 0.90 * HBM_MEASURED_GBS))
-    nvlink_min_gbs: float = field(default_factory=lambda: _env_float("B200PROBE_NVLINK_MIN_GBS", 0.90 * NVLINK_MEASURED_GBS))
+    # one dead link of 18 costs 5.6% (692 -> ~654 GB/s): the gate sits 3% under the healthy figure
+    nvlink_min_gbs: float = field(default_factory=lambda: _env_float("B200PROBE_NVLINK_MIN_GBS", 0.97 * NVLINK_HEALTHY_GBS))
     gemm_min_tflops: float = field(default_factory=lambda: _env_float("B200PROBE_GEMM_MIN_TFLOPS", 0.70 * GEMM_MEASURED_TFLOPS))
     verdict_min_bytes: int = 256 << 20        # sizes below L2 are cache-resident: never used for the verdict
 

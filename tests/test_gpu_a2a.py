@@ -23,37 +23,70 @@ def env():
     return torch, Probe(), _oracle.load()
 
 
+VARIANTS = {0: "pull-tma", 1: "push-tma", 2: "push-direct", 3: "push-buf"}
+
+
 @pytest.mark.parametrize("S", [16, 4096 + 16, 1 << 20, (3 << 20) + 48])
-@pytest.mark.parametrize("from_buf", [False, True])
-@pytest.mark.parametrize("variant", [0, 1], ids=["tma", "direct"])
-def test_push_lands_oracle_pattern_in_every_peer_window(env, S, from_buf, variant):
+@pytest.mark.parametrize("variant", sorted(VARIANTS), ids=lambda v: VARIANTS[v])
+def test_exchange_lands_oracle_pattern_in_every_recv_slot(env, S, variant):
     torch, p, o = env
     g = min(torch.cuda.device_count(), 8)
     ords = (C.c_int * g)(*range(g))
     p._check(p.lib.b200probe_enable_peer_access(ords, g), "enable_peer_access")
-    wins = [torch.full((g * S + 64,), 0x5A, dtype=torch.uint8, device=f"cuda:{r}") for r in range(g)]
+    # windows owned by the test (torch tensors): [recv g x S][send g x S] + guard bytes
+    wins = [torch.full((2 * g * S + 64,), 0x5A, dtype=torch.uint8, device=f"cuda:{r}") for r in range(g)]
     peers = (C.c_void_p * g)(*[w.data_ptr() for w in wins])
     for r in range(g):
         st = torch.cuda.current_stream(r).cuda_stream
-        if from_buf:
-            send = np.concatenate([_oracle.pattern(o, 0, S // 4, o.oracle_a2a_chunk_seed(SEED, r, d)) for d in range(g)])
-            sb = torch.from_numpy(send.view(np.uint8)).to(f"cuda:{r}")
-            p._check(p.lib.b200probe_a2a_push_buf(r, r, g, sb.data_ptr(), peers, S, 0, variant, st), "push_buf")
-        else:
-            p._check(p.lib.b200probe_a2a_push(r, r, g, peers, S, SEED, 3, variant, st), "push")
+        p._check(p.lib.b200probe_a2a_window_fill(r, wins[r].data_ptr(), r, g, S, SEED, st), "window_fill")
+    for r in range(g):
+        torch.cuda.synchronize(r)
+    # the send halves are the oracle's chunks, bit for bit
+    for r in range(g):
+        host = wins[r].cpu().numpy()
+        for d in range(g):
+            want = _oracle.pattern(o, 0, S // 4, o.oracle_a2a_chunk_seed(SEED, r, d))
+            assert np.array_equal(host[(g + d) * S:(g + d + 1) * S].view(np.uint32), want)
+    for r in range(g):
+        st = torch.cuda.current_stream(r).cuda_stream
+        p._check(p.lib.b200probe_a2a_exchange(r, r, g, peers, S, SEED, variant, 3, -1, st), "exchange")
     for r in range(g):
         torch.cuda.synchronize(r)
     for dst in range(g):
         host = wins[dst].cpu().numpy()
-        assert (host[g * S:] == 0x5A).all(), "wrote past the window"
+        assert (host[2 * g * S:] == 0x5A).all(), "wrote past the window"
         for src in range(g):
             want = _oracle.pattern(o, 0, S // 4, o.oracle_a2a_chunk_seed(SEED, src, dst))
             got = host[src * S:(src + 1) * S].view(np.uint32)
-            assert np.array_equal(got, want), f"chunk {src}->{dst} differs from oracle"
+            assert np.array_equal(got, want), f"chunk {src}->{dst} differs from oracle ({VARIANTS[variant]})"
             assert p.lib.b200probe_a2a_chunk_seed(SEED, src, dst) == o.oracle_a2a_chunk_seed(SEED, src, dst)
 
 
-@pytest.mark.parametrize("variant", [0, 1], ids=["tma", "direct"])
+def test_only_peer_selectors(env):
+    torch, p, o = env
+    g = min(torch.cuda.device_count(), 8)
+    S = 1 << 16
+    ords = (C.c_int * g)(*range(g))
+    p._check(p.lib.b200probe_enable_peer_access(ords, g), "enable_peer_access")
+    wins = [torch.zeros(2 * g * S, dtype=torch.uint8, device=f"cuda:{r}") for r in range(g)]
+    peers = (C.c_void_p * g)(*[w.data_ptr() for w in wins])
+    for r in range(g):
+        p._check(p.lib.b200probe_a2a_window_fill(r, wins[r].data_ptr(), r, g, S, SEED, torch.cuda.current_stream(r).cuda_stream), "fill")
+        torch.cuda.synchronize(r)
+    st0 = torch.cuda.current_stream(0).cuda_stream
+    p._check(p.lib.b200probe_a2a_exchange(0, 0, g, peers, S, SEED, 0, 0, -2, st0), "exchange -2")     # peers only
+    torch.cuda.synchronize(0)
+    host = wins[0].cpu().numpy()
+    assert not host[0:S].any(), "-2 must not touch the local slot"
+    assert host[S:2 * S].any()
+    from k3s_nvidia_b200.probe import ProbeError
+    with pytest.raises(ProbeError):
+        p._check(p.lib.b200probe_a2a_exchange(0, 0, g, peers, S + 4, SEED, 0, 0, -1, st0), "bad S")
+    with pytest.raises(ProbeError):
+        p._check(p.lib.b200probe_a2a_exchange(0, 0, g, peers, S, SEED, 9, 0, -1, st0), "bad variant")
+
+
+@pytest.mark.parametrize("variant", sorted(VARIANTS), ids=lambda v: VARIANTS[v])
 @pytest.mark.parametrize("mode", [0, 1, 2], ids=["peer-all", "peer-pair", "nccl"])
 def test_single_process_probe_verifies_and_reports(env, mode, variant):
     torch, p, o = env
@@ -64,7 +97,7 @@ def test_single_process_probe_verifies_and_reports(env, mode, variant):
         for j in range(g):
             assert (rep.pair_gbs[i][j] > 0) == (i != j)
     if mode != 1:
-        assert all(x > 0 for x in rep.egress_gbs) and rep.ms_median > 0
+        assert all(x > 0 for x in rep.egress_gbs) and all(x > 0 for x in rep.ingress_gbs) and rep.ms_median > 0
 
 
 def test_full_size_exchange_properties(env):
@@ -76,5 +109,5 @@ def test_full_size_exchange_properties(env):
     a = p.nvlink_a2a(list(range(g)), bytes_per_pair=256 << 20, warmup=2, reps=5, verify=1)
     b = p.nvlink_a2a(list(range(g)), bytes_per_pair=256 << 20, warmup=2, reps=5, verify=1)
     assert a.verified == 1 and b.verified == 1
-    for x, y in zip(a.egress_gbs, b.egress_gbs):
+    for x, y in zip(a.ingress_gbs[:g], b.ingress_gbs[:g]):
         assert abs(x - y) / max(x, y) < 0.05
