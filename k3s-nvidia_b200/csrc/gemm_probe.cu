@@ -18,6 +18,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <cstdlib>
 #include <vector>
 
 #include "common.h"
@@ -226,6 +227,169 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
     }
 }
 
+// ---- cta_group::2 (CTA pair) forms -------------------------------------------------------------
+constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;     // shared::cluster address of the same offset in the even (leader) CTA
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// both CTAs of the pair issue their loads; the bytes complete on the LEADER's mbarrier
+__device__ __forceinline__ void tma_load_2d_2sm(uint32_t dst_smem, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst_smem),
+                 "l"((uint64_t)map), "r"(bar & kPeerBitMask), "r"(c0), "r"(c1)
+                 : "memory");
+}
+__device__ __forceinline__ void umma_bf16_2sm(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+        "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// arrive on the mbarrier at this offset in BOTH CTAs of the pair when the issued MMAs retire
+__device__ __forceinline__ void umma_commit_2sm(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"((uint16_t)3)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_leader(uint32_t bar) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar & kPeerBitMask) : "memory");
+}
+constexpr int STAGES2 = 6;
+constexpr int A2_STAGE_BYTES = BM * BK * 2;             // this CTA's 128 rows of the 256-row A tile
+constexpr int B2_STAGE_BYTES = (BN / 2) * BK * 2;       // this CTA's 128 of the 256 B rows
+constexpr int STAGE2_BYTES = A2_STAGE_BYTES + B2_STAGE_BYTES;     // 32 KiB per CTA per stage
+constexpr int SMEM2_BYTES = STAGES2 * STAGE2_BYTES + 1024 + 256;
+constexpr uint32_t kIdesc2 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((2 * BM) >> 4) << 24);   // M = 256
+
+__device__ __forceinline__ TileCoord tile_coord2(int t, int num_m, int num_n) {     // tiles of (2*BM) x BN
+    const int per_band = (GROUP_M / 2) * num_n;
+    const int band = t / per_band;
+    const int first_m = band * (GROUP_M / 2);
+    const int rows = min(GROUP_M / 2, num_m - first_m);
+    const int in_band = t - band * per_band;
+    return {(first_m + in_band % rows) * 2 * BM, (in_band / rows) * BN};
+}
+
+// C tile 256 x 256 per CTA PAIR: UMMA M=256 N=256 K=16 with cta_group::2.  Each CTA stages its own
+// 128 A rows and 128 of the 256 B rows (half the shared-memory fill and L2 traffic per flop of the
+// 1-CTA kernel), holds its 128 accumulator rows in its own TMEM and runs its own epilogue.
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
+gemm_bf16_tn_2cta_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, __nv_bfloat16* __restrict__ C,
+                         int M, int N, int K) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint8_t* smem_a = smem;
+    uint8_t* smem_b = smem + STAGES2 * A2_STAGE_BYTES;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES2 * STAGE2_BYTES);
+    uint64_t* full = bars;                   // [STAGES2]  used in the leader only
+    uint64_t* empty = bars + STAGES2;        // [STAGES2]  one per CTA, signalled by multicast commit
+    uint64_t* tfull = bars + 2 * STAGES2;    // [2]        one per CTA, signalled by multicast commit
+    uint64_t* tempty = tfull + 2;            // [2]        used in the leader only: 8 epilogue warps arrive
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t cta_rank = cluster_ctarank();
+    const bool leader = cta_rank == 0;
+    const int num_m = M / (2 * BM), num_n = N / BN, num_tiles = num_m * num_n, num_kb = K / BK;
+    const int pair = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tma_a) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tma_b) : "memory");
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < STAGES2; ++s) { mbar_init(smem_u32(&full[s]), 1); mbar_init(smem_u32(&empty[s]), 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(smem_u32(&tfull[a]), 1); mbar_init(smem_u32(&tempty[a]), 8); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {                                   // ===== TMA producer (both CTAs) =====
+            uint32_t stage = 0, phase = 0;
+            for (int t = pair; t < num_tiles; t += num_pairs) {
+                const TileCoord tc = tile_coord2(t, num_m, num_n);
+                const int my_m = tc.m0 + (int)cta_rank * BM, my_n = tc.n0 + (int)cta_rank * (BN / 2);
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    mbar_wait(smem_u32(&empty[stage]), phase ^ 1);
+                    const uint32_t fb = smem_u32(&full[stage]);
+                    if (leader) mbar_expect_tx(fb, 2 * STAGE2_BYTES);      // both CTAs' bytes land on the leader's barrier
+                    tma_load_2d_2sm(smem_u32(smem_a + stage * A2_STAGE_BYTES), &tma_a, fb, kb * BK, my_m);
+                    tma_load_2d_2sm(smem_u32(smem_b + stage * B2_STAGE_BYTES), &tma_b, fb, kb * BK, my_n);
+                    if (++stage == STAGES2) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (leader && lane == 0) {                         // ===== MMA issuer (leader CTA only) =====
+            uint32_t stage = 0, phase = 0, it = 0;
+            for (int t = pair; t < num_tiles; t += num_pairs, ++it) {
+                const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
+                mbar_wait(smem_u32(&tempty[acc]), acc_phase ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + acc * BN;
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    mbar_wait(smem_u32(&full[stage]), phase);
+                    tc_fence_after();
+                    const uint64_t a_desc = make_smem_desc(smem_u32(smem_a + stage * A2_STAGE_BYTES));
+                    const uint64_t b_desc = make_smem_desc(smem_u32(smem_b + stage * B2_STAGE_BYTES));
+#pragma unroll
+                    for (int k = 0; k < BK / UMMA_K; ++k)
+                        umma_bf16_2sm(d_tmem, a_desc + (uint64_t)(k * 2), b_desc + (uint64_t)(k * 2), kIdesc2, (kb | k) != 0);
+                    umma_commit_2sm(smem_u32(&empty[stage]));
+                    if (++stage == STAGES2) { stage = 0; phase ^= 1; }
+                }
+                umma_commit_2sm(smem_u32(&tfull[acc]));
+            }
+        }
+    } else if (warp >= 4) {                                // ===== epilogue (both CTAs, own 128 rows) =====
+        const int q = warp - 4;
+        uint32_t it = 0;
+        for (int t = pair; t < num_tiles; t += num_pairs, ++it) {
+            const TileCoord tc = tile_coord2(t, num_m, num_n);
+            const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
+            mbar_wait(smem_u32(&tfull[acc]), acc_phase);
+            tc_fence_after();
+            const int row = tc.m0 + (int)cta_rank * BM + q * 32 + lane;
+            __nv_bfloat16* crow = C + (size_t)row * N + tc.n0;
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN;
+#pragma unroll 1
+            for (int c = 0; c < BN / 32; ++c) {
+                uint32_t v[32];
+                tmem_ld_32x32(taddr + c * 32, v);
+                tmem_ld_wait();
+                uint32_t pk[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    __nv_bfloat162 h = __floats2bfloat162_rn(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]));
+                    pk[j] = *reinterpret_cast<uint32_t*>(&h);
+                }
+                uint4* dst = reinterpret_cast<uint4*>(crow + c * 32);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) dst[j] = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_leader(smem_u32(&tempty[acc]));
+        }
+    }
+    tc_fence_before();
+    cluster_sync_all();            // the peer's MMAs read this CTA's shared memory: nobody leaves early
+    if (warp == 2) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
+    }
+}
+
 __global__ void gemm_fill_kernel(uint16_t* dst, uint64_t elems, uint32_t seed, int which) {
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
@@ -332,6 +496,18 @@ int b200probe_gemm_fill(int ordinal, void* dst, uint64_t elems, uint32_t seed, i
     return 0;
 }
 
+// kernel variant: 2 = CTA-pair kernel (default when M is a multiple of 256), 1 = single-CTA kernel.
+// B200PROBE_GEMM_VARIANT overrides (tuning / A-B comparison).
+static int gemm_variant_for(int m) {
+    static int forced = -1;
+    if (forced < 0) {
+        const char* e = getenv("B200PROBE_GEMM_VARIANT");
+        forced = e ? atoi(e) : 0;
+    }
+    if (forced == 1) return 1;
+    return (m % (2 * BM) == 0) ? 2 : 1;
+}
+
 int b200probe_gemm_launch(int ordinal, const void* a, const void* b, void* c, int m, int n, int k, void* stream) {
     b200::DevProps props;
     int rc = b200::device_props(ordinal, &props);
@@ -340,19 +516,23 @@ int b200probe_gemm_launch(int ordinal, const void* a, const void* b, void* c, in
     if (rc) return rc;
     if (!a || !b || !c || (((uintptr_t)a | (uintptr_t)b | (uintptr_t)c) & 15)) { b200::set_error("gemm: operands must be 16-byte aligned device pointers"); return B200PROBE_EINVAL; }
     B200_CUDA_TRY(cudaSetDevice(ordinal));
+    const int variant = gemm_variant_for(m);
     CUtensorMap ma, mb;
     rc = make_map(&ma, a, m, k, BM);
     if (rc) return rc;
-    rc = make_map(&mb, b, n, k, BN);
+    rc = make_map(&mb, b, n, k, variant == 2 ? BN / 2 : BN);
     if (rc) return rc;
-    static bool attr_set[B200PROBE_MAX_DEVICES] = {false};
-    if (!attr_set[ordinal]) {
+    if (variant == 2) {
+        B200_CUDA_TRY(cudaFuncSetAttribute(gemm_bf16_tn_2cta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM2_BYTES));
+        const int tiles = (m / (2 * BM)) * (n / BN);
+        const int pairs = std::min(tiles, props.sms / 2);
+        gemm_bf16_tn_2cta_kernel<<<2 * pairs, NUM_THREADS, SMEM2_BYTES, (cudaStream_t)stream>>>(ma, mb, (__nv_bfloat16*)c, m, n, k);
+    } else {
         B200_CUDA_TRY(cudaFuncSetAttribute(gemm_bf16_tn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-        attr_set[ordinal] = true;
+        const int tiles = (m / BM) * (n / BN);
+        const int grid = std::min(tiles, props.sms);
+        gemm_bf16_tn_kernel<<<grid, NUM_THREADS, SMEM_BYTES, (cudaStream_t)stream>>>(ma, mb, (__nv_bfloat16*)c, m, n, k);
     }
-    const int tiles = (m / BM) * (n / BN);
-    const int grid = std::min(tiles, props.sms);
-    gemm_bf16_tn_kernel<<<grid, NUM_THREADS, SMEM_BYTES, (cudaStream_t)stream>>>(ma, mb, (__nv_bfloat16*)c, m, n, k);
     B200_CUDA_TRY(cudaGetLastError());
     return 0;
 }
