@@ -175,11 +175,13 @@ int b200probe_hbm_copy_host(int cuda_ordinal, const void* src_host, void* dst_ho
 #define B200PROBE_A2A_PEER_PAIR   1   /* same kernel, one (src,dst) pair at a time -> matrix       */
 #define B200PROBE_A2A_NCCL        2   /* grouped ncclSend/ncclRecv (the library leg, for contrast) */
 /* exchange kernels (cfg.variant) */
-#define B200PROBE_A2A_PULL_TMA    0   /* bulk-LOAD the peers' send chunks over NVLink (default: reads
-                                         move 781 GB/s per direction on B200, writes 712)           */
-#define B200PROBE_A2A_PUSH_TMA    1   /* generate in shared memory, bulk-STORE into the peers       */
-#define B200PROBE_A2A_PUSH_DIRECT 2   /* generate in registers, 16-byte stores on peer pointers     */
-#define B200PROBE_A2A_PUSH_BUF    3   /* bulk-load the local send chunk, bulk-store into the peer   */
+#define B200PROBE_A2A_AUTO        0   /* PUSH_TMA for the concurrent exchange, PULL_TMA for one pair */
+#define B200PROBE_A2A_PULL_TMA    1   /* bulk-LOAD the peers' send chunks over NVLink: best one-way
+                                         (756-781 GB/s), worse when both directions are loaded (626) */
+#define B200PROBE_A2A_PUSH_TMA    2   /* generate in shared memory, bulk-STORE into the peers: best
+                                         for the all-to-all (692 GB/s per direction per GPU)         */
+#define B200PROBE_A2A_PUSH_DIRECT 3   /* generate in registers, 16-byte stores on peer pointers     */
+#define B200PROBE_A2A_PUSH_BUF    4   /* bulk-load the local send chunk, bulk-store into the peer   */
 
 typedef struct b200probe_a2a_cfg {
     uint64_t bytes_per_pair;        /* S, multiple of 16; 0 = 256 MiB                              */
@@ -188,7 +190,7 @@ typedef struct b200probe_a2a_cfg {
     uint32_t seed;
     int      verify;
     int      ctas_per_peer;         /* 0 = default (about one CTA per SM in total)                 */
-    int      variant;               /* B200PROBE_A2A_PULL_TMA ...                                  */
+    int      variant;               /* B200PROBE_A2A_AUTO ...                                      */
 } b200probe_a2a_cfg_t;
 
 typedef struct b200probe_a2a_result {

@@ -5,10 +5,13 @@
 //   recv[p] = where rank p's chunk for this rank lands
 // Windows are peer-mapped (cudaDeviceEnablePeerAccess in one process, cudaIpc* across processes)
 // and the exchange is done by OUR kernels over those mappings — no NCCL on the data path:
-//   PULL_TMA    (default) each rank bulk-LOADS its peers' send chunks over NVLink into shared
-//               memory (cp.async.bulk, SASS UBLKCP) and bulk-stores them into its own recv slots.
-//               Reads move 781 GB/s per direction on B200; writes only 712 (profiles/p2p_pull_tune_r01.txt)
-//   PUSH_TMA    pattern generated into shared memory, bulk-STORED into the peers' recv slots
+//   PUSH_TMA    pattern generated into shared memory, bulk-STORED (cp.async.bulk, SASS UBLKCP) into the
+//               peers' recv slots.  Best when BOTH directions are loaded (the all-to-all): 692 GB/s
+//               per direction per GPU on B200 vs 626 for pulls (profiles/a2a_tune_r01_2gpu_variants.txt)
+//   PULL_TMA    each rank bulk-LOADS its peers' send chunks over NVLink into shared memory and
+//               bulk-stores them into its own recv slots.  Best for ONE direction at a time (the
+//               pairwise matrix): 756-781 GB/s vs 699-712 for writes (profiles/p2p_pull_tune_r01.txt)
+//   AUTO        (default) PUSH_TMA for the concurrent exchange, PULL_TMA for an isolated pair
 //   PUSH_DIRECT pattern generated in registers, 16-byte stores on the peer pointers
 //   PUSH_BUF    local send chunk bulk-loaded, bulk-stored to the peer
 // CTAs are partitioned per peer so every peer's traffic is in flight at once (NVSwitch gives each
@@ -170,6 +173,7 @@ int launch_exchange(int ordinal, int rank, int world, void* const* windows, uint
     if (world < 1 || world > kMaxWorld || rank < 0 || rank >= world || !windows) { b200::set_error("a2a: bad rank/world"); return B200PROBE_EINVAL; }
     if (S & 15) { b200::set_error("a2a: bytes_per_pair must be a multiple of 16"); return B200PROBE_EINVAL; }
     if (variant < 0 || variant > B200PROBE_A2A_PUSH_BUF) { b200::set_error("a2a: unknown variant %d", variant); return B200PROBE_EINVAL; }
+    if (variant == B200PROBE_A2A_AUTO) variant = only_peer >= 0 ? B200PROBE_A2A_PULL_TMA : B200PROBE_A2A_PUSH_TMA;
     if (only_peer >= world) { b200::set_error("a2a: peer %d out of range", only_peer); return B200PROBE_ERANGE; }
     b200::DevProps props;
     int rc = b200::device_props(ordinal, &props);
@@ -363,6 +367,7 @@ int b200probe_nvlink_a2a(const int* ordinals, int g, const b200probe_a2a_cfg_t* 
     out->verified = -1;
     if (pair_gbs) std::fill(pair_gbs, pair_gbs + g * g, 0.0);
     const bool nccl_mode = cfg.mode == B200PROBE_A2A_NCCL;
+    if (cfg.variant == B200PROBE_A2A_AUTO) cfg.variant = cfg.mode == B200PROBE_A2A_PEER_PAIR ? B200PROBE_A2A_PULL_TMA : B200PROBE_A2A_PUSH_TMA;
     const bool pull = !nccl_mode && cfg.variant == B200PROBE_A2A_PULL_TMA;
 
     int rc = b200probe_enable_peer_access(ordinals, g);

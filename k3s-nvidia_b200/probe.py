@@ -211,7 +211,7 @@ class Probe:
 
     # -- NVLink ----------------------------------------------------------------------------------
     def nvlink_a2a(self, ordinals: Sequence[int], *, bytes_per_pair=None, mode=L.A2A_PEER_ALL, warmup=None, reps=None,
-                   seed=0xB200, verify=1, ctas_per_peer=None, variant=L.A2A_PULL_TMA) -> A2aReport:
+                   seed=0xB200, verify=1, ctas_per_peer=None, variant=L.A2A_AUTO) -> A2aReport:
         g = len(ordinals)
         cfg = L.A2aCfg()
         cfg.bytes_per_pair = bytes_per_pair or 0

@@ -23,7 +23,7 @@ def env():
     return torch, Probe(), _oracle.load()
 
 
-VARIANTS = {0: "pull-tma", 1: "push-tma", 2: "push-direct", 3: "push-buf"}
+VARIANTS = {0: "auto", 1: "pull-tma", 2: "push-tma", 3: "push-direct", 4: "push-buf"}
 
 
 @pytest.mark.parametrize("S", [16, 4096 + 16, 1 << 20, (3 << 20) + 48])

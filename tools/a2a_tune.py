@@ -9,13 +9,13 @@ ords = list(range(g))
 out = []
 for mode in (0, 1, 2):
     for S in (1 << 20, 16 << 20, 256 << 20):
-        for variant in ((0, 1, 2, 3) if mode != 2 else (0,)):
+        for variant in ((1, 2, 3, 4) if mode != 2 else (0,)):
             try:
                 r = p.nvlink_a2a(ords, bytes_per_pair=S, mode=mode, warmup=2, reps=8, variant=variant)
                 out.append(f"mode={mode} variant={variant} S={S>>20}MiB ms={r.ms_median:.4f} egress={[round(x,1) for x in r.egress_gbs]} ingress={[round(x,1) for x in r.ingress_gbs]} pair_min={r.min_pair_gbs:.1f} pair_max={r.max_pair_gbs:.1f} verified={r.verified}")
             except Exception as e:
                 out.append(f"mode={mode} variant={variant} S={S>>20}MiB ERR {e}")
-for variant, cands in ((0, (8, 16, 37, 74, 148, 296)), (1, (37, 74, 148)), (2, (148, 592))):
+for variant, cands in ((1, (37, 148)), (2, (18, 37, 74, 148, 296)), (3, (148, 592))):
     for c in cands:
         r = p.nvlink_a2a(ords, bytes_per_pair=256 << 20, mode=0, warmup=2, reps=8, ctas_per_peer=c, variant=variant)
         out.append(f"tune variant={variant} ctas_per_peer={c} egress={[round(x,1) for x in r.egress_gbs]} ingress={[round(x,1) for x in r.ingress_gbs]}")
