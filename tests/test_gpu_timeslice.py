@@ -1,0 +1,21 @@
+"""BASELINE config 4: values.yaml time-slicing replicas=4 -> four concurrent probe processes on one
+B200; aggregate HBM GB/s over a common window, and every process's data result is still exact."""
+import pytest
+
+import _oracle
+
+pytestmark = pytest.mark.gpu
+
+
+def test_four_probe_processes_share_one_gpu():
+    from k3s_nvidia_b200 import timeslice
+
+    nbytes = 256 << 20
+    r = timeslice.run(replicas=4, ordinal=0, nbytes=nbytes, window_s=2.0)
+    assert r["replicas"] == 4 and len(r["workers"]) == 4
+    o = _oracle.load()
+    for w in r["workers"]:
+        assert (w["sum64"], w["xor32"]) == _oracle.pattern_checksum(o, nbytes // 4, 0xB200 + w["worker"])
+        assert w["launches"] > 0
+    # time-slicing serialises the contexts: the aggregate stays near one process's bandwidth
+    assert r["aggregate_gbs"] > 3000, r
