@@ -113,6 +113,20 @@ int  b200probe_passive_health(int timeout_ms, uint64_t* unhealthy_mask);
 int  b200probe_health_mask(uint64_t* unhealthy_mask);
 void b200probe_health_close(void);
 
+/* ---- passive NVLink / fabric status ------------------------------------------- */
+typedef struct b200probe_nvlink_status {
+    int      links_total;           /* links NVML reports a state for (18 on a B200)               */
+    int      links_active;
+    uint32_t active_mask;           /* bit l = link l is up                                        */
+    int      fabric_state;          /* nvmlGpuFabricState_t (3 = completed); -1 = not supported    */
+    int      fabric_status;         /* nvmlReturn_t of the fabric registration                     */
+    uint32_t fabric_health_mask;
+    uint64_t data_tx_kib, data_rx_kib;   /* payload counters, summed over links, since driver load */
+    uint64_t raw_tx_kib, raw_rx_kib;     /* payload + protocol overhead                            */
+    int      counters_ok;
+} b200probe_nvlink_status_t;
+int b200probe_nvlink_passive(int idx, b200probe_nvlink_status_t* out);
+
 /* ---- HBM bandwidth sweep (row a11) ------------------------------------------------------------ */
 #define B200PROBE_HBM_READ   1
 #define B200PROBE_HBM_WRITE  2

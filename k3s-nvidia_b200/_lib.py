@@ -53,6 +53,22 @@ class HealthEvent(C.Structure):
     ]
 
 
+class NvlinkStatus(C.Structure):
+    _fields_ = [
+        ("links_total", C.c_int),
+        ("links_active", C.c_int),
+        ("active_mask", C.c_uint32),
+        ("fabric_state", C.c_int),
+        ("fabric_status", C.c_int),
+        ("fabric_health_mask", C.c_uint32),
+        ("data_tx_kib", C.c_uint64),
+        ("data_rx_kib", C.c_uint64),
+        ("raw_tx_kib", C.c_uint64),
+        ("raw_rx_kib", C.c_uint64),
+        ("counters_ok", C.c_int),
+    ]
+
+
 class HbmCfg(C.Structure):
     _fields_ = [
         ("min_bytes", C.c_uint64),
@@ -164,6 +180,7 @@ SIGNATURES = {
     "b200probe_passive_health": (C.c_int, [C.c_int, _P(C.c_uint64)]),
     "b200probe_health_mask": (C.c_int, [_P(C.c_uint64)]),
     "b200probe_health_close": (None, []),
+    "b200probe_nvlink_passive": (C.c_int, [C.c_int, _P(NvlinkStatus)]),
     "b200probe_hbm_sweep": (C.c_int, [C.c_int, _P(HbmCfg), _P(HbmResult), C.c_int, _P(C.c_int)]),
     "b200probe_hbm_release": (C.c_int, [C.c_int]),
     "b200probe_hbm_fill": (C.c_int, [C.c_int, _vp, C.c_uint64, C.c_uint32, _P(HbmCfg), _vp]),

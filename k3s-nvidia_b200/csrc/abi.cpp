@@ -40,6 +40,9 @@ struct Nvml {
     nvmlReturn_t (*EventSetCreate)(nvmlEventSet_t*);
     nvmlReturn_t (*EventSetWait_v2)(nvmlEventSet_t, nvmlEventData_t*, unsigned int);
     nvmlReturn_t (*EventSetFree)(nvmlEventSet_t);
+    nvmlReturn_t (*DeviceGetNvLinkState)(nvmlDevice_t, unsigned int, nvmlEnableState_t*);    // optional
+    nvmlReturn_t (*DeviceGetFieldValues)(nvmlDevice_t, int, nvmlFieldValue_t*);              // optional
+    nvmlReturn_t (*DeviceGetGpuFabricInfoV)(nvmlDevice_t, nvmlGpuFabricInfoV_t*);            // optional
 };
 
 struct Device {
@@ -343,6 +346,9 @@ int b200probe_init(const char* path) {
     sym(lib, "nvmlDeviceGetPciInfo_v3", n.DeviceGetPciInfo_v3, false);
     sym(lib, "nvmlDeviceGetNumaNodeId", n.DeviceGetNumaNodeId, false);
     sym(lib, "nvmlDeviceGetMigMode", n.DeviceGetMigMode, false);
+    sym(lib, "nvmlDeviceGetNvLinkState", n.DeviceGetNvLinkState, false);
+    sym(lib, "nvmlDeviceGetFieldValues", n.DeviceGetFieldValues, false);
+    sym(lib, "nvmlDeviceGetGpuFabricInfoV", n.DeviceGetGpuFabricInfoV, false);
     if (!ok) { dlclose(lib); return B200PROBE_ENVML; }
     nvmlReturn_t r = n.Init_v2();
     if (r != NVML_SUCCESS) { b200::set_error("nvmlInit_v2: %s", n.ErrorString(r)); dlclose(lib); return nvml_rc(r); }
@@ -472,6 +478,59 @@ void b200probe_health_close(void) {
     g.evset = nullptr;
     g.health_open = g.health_disabled = false;
     g.unhealthy = 0;
+}
+
+// Passive NVLink cross-check: per-link state (nvml.h:8766), fabric registration
+// + health mask (nvml.h:7220, :3453-3488) and the DATA/RAW throughput counters (nvml.h:2383-2386).
+// Correlated with the active all-to-all by the host: a cold row in the pair matrix + an inactive
+// link localises the fault; RAW-DATA counter deltas around an exchange give the protocol overhead.
+int b200probe_nvlink_passive(int idx, b200probe_nvlink_status_t* out) {
+    if (!out) return B200PROBE_EINVAL;
+    Lock l;
+    if (!g.inited) return B200PROBE_ENOTINIT;
+    if (idx < 0 || idx >= (int)g.devs.size()) return B200PROBE_ERANGE;
+    memset(out, 0, sizeof(*out));
+    out->fabric_state = -1;
+    nvmlDevice_t h = g.devs[idx].h;
+    if (g.nvml.DeviceGetNvLinkState) {
+        for (unsigned link = 0; link < NVML_NVLINK_MAX_LINKS; ++link) {
+            nvmlEnableState_t st;
+            nvmlReturn_t r = g.nvml.DeviceGetNvLinkState(h, link, &st);
+            if (r != NVML_SUCCESS) continue;          // NOT_SUPPORTED / INVALID_ARGUMENT: link does not exist
+            out->links_total++;
+            if (st == NVML_FEATURE_ENABLED) { out->links_active++; out->active_mask |= 1u << link; }
+        }
+    }
+    if (g.nvml.DeviceGetGpuFabricInfoV) {
+        nvmlGpuFabricInfoV_t fi;
+        memset(&fi, 0, sizeof(fi));
+        fi.version = nvmlGpuFabricInfo_v2;
+        if (g.nvml.DeviceGetGpuFabricInfoV(h, &fi) == NVML_SUCCESS) {
+            out->fabric_state = (int)fi.state;
+            out->fabric_status = (int)fi.status;
+            out->fabric_health_mask = fi.healthMask;
+        }
+    }
+    if (g.nvml.DeviceGetFieldValues) {
+        nvmlFieldValue_t fv[4];
+        memset(fv, 0, sizeof(fv));
+        const unsigned ids[4] = {NVML_FI_DEV_NVLINK_THROUGHPUT_DATA_TX, NVML_FI_DEV_NVLINK_THROUGHPUT_DATA_RX, NVML_FI_DEV_NVLINK_THROUGHPUT_RAW_TX,
+                                 NVML_FI_DEV_NVLINK_THROUGHPUT_RAW_RX};
+        for (int i = 0; i < 4; ++i) { fv[i].fieldId = ids[i]; fv[i].scopeId = 0xFFFFFFFFu; }   // UINT_MAX: sum over all links
+        if (g.nvml.DeviceGetFieldValues(h, 4, fv) == NVML_SUCCESS) {
+            uint64_t v[4];
+            int ok = 1;
+            for (int i = 0; i < 4; ++i) {
+                if (fv[i].nvmlReturn != NVML_SUCCESS) { ok = 0; v[i] = 0; continue; }
+                v[i] = fv[i].valueType == NVML_VALUE_TYPE_UNSIGNED_LONG_LONG ? fv[i].value.ullVal
+                     : fv[i].valueType == NVML_VALUE_TYPE_UNSIGNED_LONG ? fv[i].value.ulVal
+                     : fv[i].valueType == NVML_VALUE_TYPE_UNSIGNED_INT ? fv[i].value.uiVal : 0;
+            }
+            out->data_tx_kib = v[0]; out->data_rx_kib = v[1]; out->raw_tx_kib = v[2]; out->raw_rx_kib = v[3];
+            out->counters_ok = ok;
+        }
+    }
+    return 0;
 }
 
 uint32_t b200probe_pattern_word(uint64_t i, uint32_t seed) { return b200_pattern_word(i, seed); }

@@ -124,6 +124,40 @@ def nvlink_labels(rep, th: Thresholds) -> Dict[str, str]:
     return out
 
 
+def nvlink_passive_labels(per_gpu: Dict[int, dict], expected_links: int = 18) -> Dict[str, str]:
+    """per_gpu: NVML index -> Probe.nvlink_passive() dict.  Every link NVML knows must be up and the
+    fabric registration completed with a clean health mask."""
+    out: Dict[str, str] = {}
+    all_ok = True
+    for idx, st in sorted(per_gpu.items()):
+        if st["links_total"] == 0:
+            continue                                   # no NVLink on this part: nothing to assert
+        ok = st["links_active"] == st["links_total"] and st["links_total"] >= expected_links
+        # fabric: a completed registration must have succeeded, and the 2-bit DEGRADED_BW field of the
+        # health mask (nvml.h:3453) must not read TRUE (1).  NOT_SUPPORTED / not started is not a fault.
+        if st["fabric_state"] == 3 and st["fabric_status"] != 0:
+            ok = False
+        if (st["fabric_health_mask"] & 0x3) == 1:
+            ok = False
+        out[f"{PREFIX}gpu{idx}.nvlink-links-active"] = str(st["links_active"])
+        out[f"{PREFIX}gpu{idx}.nvlink-links-total"] = str(st["links_total"])
+        out[f"{PREFIX}gpu{idx}.nvlink-links-ok"] = _b(ok)
+        all_ok = all_ok and ok
+    if out:
+        out[f"{PREFIX}nvlink-links-ok"] = _b(all_ok)
+    return out
+
+
+def wire_efficiency(before: dict, after: dict):
+    """payload / raw bytes on the wire between two passive snapshots (None when the counters are not
+    readable): NVML's DATA vs RAW counters quantify the protocol overhead of the active exchange."""
+    if not (before.get("counters_ok") and after.get("counters_ok")):
+        return None
+    d = after["data_tx_kib"] - before["data_tx_kib"]
+    r = after["raw_tx_kib"] - before["raw_tx_kib"]
+    return (d / r) if r > 0 else None
+
+
 def gemm_labels(per_gpu: Dict[int, object], th: Thresholds) -> Dict[str, str]:
     out: Dict[str, str] = {}
     all_ok = True
@@ -227,9 +261,21 @@ class ActiveProbeRunner:
                     got[f"{PREFIX}gemm-healthy"] = "false"
                 labels.update(got)
         ords = [d.cuda_ordinal for d in [self.probe.device_info(i) for i in range(n)] if d.cuda_ordinal >= 0]
+        passive_before = {}
+        try:
+            passive_before = {d.index: self.probe.nvlink_passive(d.index) for d in infos}
+            labels.update(nvlink_passive_labels(passive_before))
+        except Exception as e:  # noqa: BLE001
+            log.error("passive NVLink status failed: %s", e)
         if self.run_nvlink and len(ords) >= 2:
             try:
                 labels.update(nvlink_labels(self.probe.nvlink_a2a(ords, warmup=1, reps=3), self.th))
+                if labels.get(f"{PREFIX}nvlink-links-ok") == "false":
+                    labels[f"{PREFIX}nvlink-healthy"] = "false"      # a dead link fails the gate even if the matrix still clears the bar
+                eff = [wire_efficiency(passive_before[d.index], self.probe.nvlink_passive(d.index)) for d in infos if d.index in passive_before]
+                eff = [e for e in eff if e]
+                if eff:
+                    labels[f"{PREFIX}nvlink-data-over-raw-pct"] = str(int(round(100.0 * min(eff))))
             except Exception as e:  # noqa: BLE001
                 log.error("NVLink probe failed: %s", e)
                 labels[f"{PREFIX}nvlink-healthy"] = "false"

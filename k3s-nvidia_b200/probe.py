@@ -169,6 +169,12 @@ class Probe:
     def health_close(self) -> None:
         self.lib.b200probe_health_close()
 
+    # -- passive NVLink ------------------------------------------------------------------------------
+    def nvlink_passive(self, idx: int) -> dict:
+        st = L.NvlinkStatus()
+        self._check(self.lib.b200probe_nvlink_passive(idx, C.byref(st)), "nvlink_passive")
+        return {f: getattr(st, f) for f, _ in L.NvlinkStatus._fields_}
+
     # -- HBM -------------------------------------------------------------------------------------
     def hbm_sweep(self, idx: int = 0, *, min_bytes=None, max_bytes=None, modes=None, warmup=None, reps=None,
                   seed=None, variant=None, verify=1, flush_l2=None, stage_bytes=None, stages=None,

@@ -10,6 +10,7 @@
  *   MOCK_NVML_NO_EVENTS=i,j        nvmlDeviceRegisterEvents -> NOT_SUPPORTED for these
  *   MOCK_NVML_EVENTS_QUERY_FAIL=i  nvmlDeviceGetSupportedEventTypes -> UNKNOWN for these
  *   MOCK_NVML_UUID_FAIL=i          nvmlDeviceGetUUID fails for these (enumeration error path)
+ *   MOCK_NVML_LINKS_DOWN=d:l,d:l   link l of device d reports NVML_FEATURE_DISABLED
  * Events are queued with mock_nvml_push(kind, device, data) and popped one per EventSetWait:
  *   kind 0 = XID critical (data = xid), 1 = double-bit ECC, 2 = single-bit ECC,
  *   kind 3 = wait returns error `data` (nvmlReturn_t), kind 4 = XID on a device whose UUID cannot
@@ -156,6 +157,50 @@ nvmlReturn_t nvmlEventSetWait_v2(nvmlEventSet_t s, nvmlEventData_t* data, unsign
         case 4: data->device = (nvmlDevice_t)&g_dev[g_n]; data->eventType = nvmlEventTypeXidCriticalError; data->eventData = e.data; break;
         case 5: data->device = (nvmlDevice_t)&g_dev[g_n + 1]; data->eventType = nvmlEventTypeXidCriticalError; data->eventData = e.data; break;
         default: return NVML_ERROR_UNKNOWN;
+    }
+    return NVML_SUCCESS;
+}
+
+/* ---- NVLink / fabric (passive cross-checks) ---------------------------------------------------- */
+static unsigned long long g_nvl_kib[MAXD][4];   /* data_tx, data_rx, raw_tx, raw_rx */
+void mock_nvml_add_nvlink_traffic(int dev, unsigned long long data_kib) {
+    if (dev < 0 || dev >= MAXD) return;
+    g_nvl_kib[dev][0] += data_kib; g_nvl_kib[dev][1] += data_kib;
+    g_nvl_kib[dev][2] += data_kib + data_kib / 8; g_nvl_kib[dev][3] += data_kib + data_kib / 8;
+}
+nvmlReturn_t nvmlDeviceGetNvLinkState(nvmlDevice_t d, unsigned int link, nvmlEnableState_t* st) {
+    if (link >= 18) return NVML_ERROR_INVALID_ARGUMENT;
+    int i = ((mdev_t*)d)->idx;
+    *st = NVML_FEATURE_ENABLED;
+    const char* s = getenv("MOCK_NVML_LINKS_DOWN");
+    while (s && *s) {
+        char* e;
+        long dev = strtol(s, &e, 10);
+        if (*e != ':') break;
+        long l = strtol(e + 1, &e, 10);
+        if (dev == i && l == (long)link) *st = NVML_FEATURE_DISABLED;
+        s = (*e == ',') ? e + 1 : e;
+        if (*e != ',') break;
+    }
+    return NVML_SUCCESS;
+}
+nvmlReturn_t nvmlDeviceGetGpuFabricInfoV(nvmlDevice_t d, nvmlGpuFabricInfoV_t* fi) {
+    (void)d;
+    if (fi->version != nvmlGpuFabricInfo_v2) return NVML_ERROR_ARGUMENT_VERSION_MISMATCH;
+    fi->state = NVML_GPU_FABRIC_STATE_COMPLETED;
+    fi->status = NVML_SUCCESS;
+    fi->cliqueId = 1;
+    fi->healthMask = 0;
+    return NVML_SUCCESS;
+}
+nvmlReturn_t nvmlDeviceGetFieldValues(nvmlDevice_t d, int n, nvmlFieldValue_t* v) {
+    int i = ((mdev_t*)d)->idx;
+    for (int k = 0; k < n; ++k) {
+        int which = (int)v[k].fieldId - NVML_FI_DEV_NVLINK_THROUGHPUT_DATA_TX;
+        if (which < 0 || which > 3 || i >= MAXD) { v[k].nvmlReturn = NVML_ERROR_NOT_SUPPORTED; continue; }
+        v[k].nvmlReturn = NVML_SUCCESS;
+        v[k].valueType = NVML_VALUE_TYPE_UNSIGNED_LONG_LONG;
+        v[k].value.ullVal = g_nvl_kib[i][which];
     }
     return NVML_SUCCESS;
 }

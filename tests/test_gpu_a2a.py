@@ -76,9 +76,16 @@ def test_only_peer_selectors(env):
     st0 = torch.cuda.current_stream(0).cuda_stream
     p._check(p.lib.b200probe_a2a_exchange(0, 0, g, peers, S, SEED, 0, 0, -2, st0), "exchange -2")     # peers only
     torch.cuda.synchronize(0)
-    host = wins[0].cpu().numpy()
-    assert not host[0:S].any(), "-2 must not touch the local slot"
-    assert host[S:2 * S].any()
+    # AUTO + all peers = PUSH_TMA: rank 0 writes its chunks into every PEER's recv[0] slot only
+    host0, host1 = wins[0].cpu().numpy(), wins[1].cpu().numpy()
+    assert not host0[0:g * S].any(), "-2 must not touch the local slot (and a push lands nothing at home)"
+    assert host1[0:S].any() and not host1[S:g * S].any()
+    # PULL_TMA (variant 1) of one peer: rank 0 loads rank 1's send[0] into its own recv[1]
+    p._check(p.lib.b200probe_a2a_exchange(0, 0, g, peers, S, SEED, 1, 0, 1, st0), "pull peer 1")
+    torch.cuda.synchronize(0)
+    host0 = wins[0].cpu().numpy()
+    assert host0[S:2 * S].any() and not host0[0:S].any() and not host0[2 * S:g * S].any()
+    assert (host0[S:2 * S] == host1[(g + 0) * S:(g + 1) * S]).all()
     from k3s_nvidia_b200.probe import ProbeError
     with pytest.raises(ProbeError):
         p._check(p.lib.b200probe_a2a_exchange(0, 0, g, peers, S + 4, SEED, 0, 0, -1, st0), "bad S")

@@ -83,3 +83,37 @@ def test_runner_publishes_false_when_probes_cannot_run(tmp_path, monkeypatch):
         assert os.path.exists(tmp_path / "b200probe")
     finally:
         p.close()
+
+
+def test_passive_nvlink_status_and_labels(monkeypatch):
+    """per-link state + fabric health from NVML, correlated with the active matrix."""
+    import ctypes as C
+
+    import _oracle
+    from k3s_nvidia_b200.probe import Probe
+
+    monkeypatch.setenv("MOCK_NVML_DEVICES", "2")
+    monkeypatch.setenv("MOCK_NVML_LINKS_DOWN", "1:5,1:7")
+    p = Probe(_oracle.MOCK_NVML)
+    try:
+        s0, s1 = p.nvlink_passive(0), p.nvlink_passive(1)
+        assert (s0["links_total"], s0["links_active"], s0["active_mask"]) == (18, 18, (1 << 18) - 1)
+        assert (s1["links_total"], s1["links_active"]) == (18, 16) and not s1["active_mask"] & ((1 << 5) | (1 << 7))
+        assert s0["fabric_state"] == 3 and s0["counters_ok"] == 1
+        lab = L.nvlink_passive_labels({0: s0, 1: s1})
+        assert lab["nvidia.com/b200probe.gpu0.nvlink-links-ok"] == "true"
+        assert lab["nvidia.com/b200probe.gpu1.nvlink-links-ok"] == "false"
+        assert lab["nvidia.com/b200probe.gpu1.nvlink-links-active"] == "16"
+        assert lab["nvidia.com/b200probe.nvlink-links-ok"] == "false"
+        mock = C.CDLL(_oracle.MOCK_NVML)
+        mock.mock_nvml_add_nvlink_traffic.argtypes = [C.c_int, C.c_ulonglong]
+        mock.mock_nvml_add_nvlink_traffic(0, 8 << 20)
+        eff = L.wire_efficiency(s0, p.nvlink_passive(0))
+        assert abs(eff - 8 / 9) < 1e-9                       # mock: raw = data * 1.125
+        assert L.wire_efficiency({"counters_ok": 0}, s0) is None
+        # degraded-bandwidth bit of the fabric health mask fails the device
+        bad = dict(s0, fabric_health_mask=1)
+        assert L.nvlink_passive_labels({0: bad})["nvidia.com/b200probe.gpu0.nvlink-links-ok"] == "false"
+        assert L.nvlink_passive_labels({0: dict(s0, links_total=0, links_active=0)}) == {}
+    finally:
+        p.close()
