@@ -179,10 +179,15 @@ int b200probe_hbm_copy (int cuda_ordinal, const void* src, void* dst, uint64_t b
                         const b200probe_hbm_cfg_t* tuning_or_null, void* stream);
 int b200probe_hbm_read (int cuda_ordinal, const void* src, uint64_t bytes, uint64_t* partials,
                         const b200probe_hbm_cfg_t* tuning_or_null, void* stream);
-/* Host-buffer entry (the e2e form): H2D src_host -> copy kernel -> D2H into dst_host, then the
- * checksum of the device result is returned.  Buffers are plain host memory. */
+/* Host-buffer entry (the data-carrying e2e form): src_host -> H2D -> copy kernel -> checksum of what
+ * landed -> D2H into dst_host, pipelined over 8 MiB chunks on three streams so both PCIe directions
+ * and the kernel overlap.  Any host memory works; pinned buffers from b200probe_host_alloc reach the
+ * PCIe rate (pageable ones are staged by the driver).  Synchronous. */
 int b200probe_hbm_copy_host(int cuda_ordinal, const void* src_host, void* dst_host, uint64_t bytes,
                             uint64_t* sum64, uint32_t* xor32);
+/* Page-locked host memory for the entry above (cudaHostAlloc, portable across devices). */
+int b200probe_host_alloc(uint64_t bytes, void** ptr);
+int b200probe_host_free(void* ptr);
 
 /* ---- NVLink all-to-all (row a12) --------------------------------------------------------------- */
 #define B200PROBE_A2A_PEER_ALL    0   /* our peer-memory kernel, all pairs concurrently            */
@@ -196,6 +201,8 @@ int b200probe_hbm_copy_host(int cuda_ordinal, const void* src_host, void* dst_ho
                                          for the all-to-all (692 GB/s per direction per GPU)         */
 #define B200PROBE_A2A_PUSH_DIRECT 3   /* generate in registers, 16-byte stores on peer pointers     */
 #define B200PROBE_A2A_PUSH_BUF    4   /* bulk-load the local send chunk, bulk-store into the peer   */
+#define B200PROBE_A2A_MIX_TMA     5   /* each chunk moved from both ends: head pushed by its source,
+                                         tail pulled by its destination ($B200PROBE_A2A_MIX_PCT)     */
 
 typedef struct b200probe_a2a_cfg {
     uint64_t bytes_per_pair;        /* S, multiple of 16; 0 = 256 MiB                              */

@@ -17,7 +17,7 @@ IPC_HANDLE_BYTES = 64
 HBM_READ, HBM_WRITE, HBM_COPY = 1, 2, 4
 VARIANT_TMA, VARIANT_DIRECT = 0, 1
 A2A_PEER_ALL, A2A_PEER_PAIR, A2A_NCCL = 0, 1, 2
-A2A_AUTO, A2A_PULL_TMA, A2A_PUSH_TMA, A2A_PUSH_DIRECT, A2A_PUSH_BUF = 0, 1, 2, 3, 4
+A2A_AUTO, A2A_PULL_TMA, A2A_PUSH_TMA, A2A_PUSH_DIRECT, A2A_PUSH_BUF, A2A_MIX_TMA = 0, 1, 2, 3, 4, 5
 NVML_ERROR_TIMEOUT = 10
 EVENT_XID_CRITICAL = 0x8
 EVENT_DBE = 0x2
@@ -187,6 +187,8 @@ SIGNATURES = {
     "b200probe_hbm_copy": (C.c_int, [C.c_int, _vp, _vp, C.c_uint64, _P(HbmCfg), _vp]),
     "b200probe_hbm_read": (C.c_int, [C.c_int, _vp, C.c_uint64, _vp, _P(HbmCfg), _vp]),
     "b200probe_hbm_copy_host": (C.c_int, [C.c_int, _vp, _vp, C.c_uint64, _P(C.c_uint64), _P(C.c_uint32)]),
+    "b200probe_host_alloc": (C.c_int, [C.c_uint64, _P(_vp)]),
+    "b200probe_host_free": (C.c_int, [_vp]),
     "b200probe_nvlink_a2a": (C.c_int, [_P(C.c_int), C.c_int, _P(A2aCfg), _P(C.c_double), _P(A2aResult)]),
     "b200probe_enable_peer_access": (C.c_int, [_P(C.c_int), C.c_int]),
     "b200probe_a2a_window_create": (C.c_int, [C.c_int, C.c_int, C.c_uint64, _P(_vp), C.c_char_p]),

@@ -14,6 +14,9 @@
 //   AUTO        (default) PUSH_TMA for the concurrent exchange, PULL_TMA for an isolated pair
 //   PUSH_DIRECT pattern generated in registers, 16-byte stores on the peer pointers
 //   PUSH_BUF    local send chunk bulk-loaded, bulk-stored to the peer
+//   MIX_TMA     every (src,dst) chunk is moved by BOTH ends at once: the first `split` bytes are pushed
+//               by src (PUSH_TMA), the rest pulled by dst (PULL_TMA), so each link direction carries
+//               posted writes and read responses side by side (B200PROBE_A2A_MIX_PCT = pushed share)
 // CTAs are partitioned per peer so every peer's traffic is in flight at once (NVSwitch gives each
 // GPU its full port bandwidth to any mix of peers).  NCCL grouped send/recv is kept as the library
 // leg for contrast (mode B200PROBE_A2A_NCCL, dlopen'ed).
@@ -48,6 +51,8 @@ struct XArgs {
     int only_peer;     // >=0 one peer; -1 all slots incl. the local one; -2 all peers, no local slot
     int variant;
     uint32_t SB, NS;   // ring stage bytes / stages
+    uint64_t split;    // MIX_TMA: bytes [0,split) of every chunk are pushed by its source, [split,S) pulled by its destination
+    int push_ctas;     // MIX_TMA: CTAs (of ctas_per_peer) in the push role
 };
 
 __device__ __forceinline__ bool cta_peer(const XArgs& a, int* peer, int* sub) {
@@ -77,26 +82,37 @@ __global__ void __launch_bounds__(kRingWarps * 32) a2a_ring_kernel(XArgs a) {
     const uint32_t SB = a.SB, NS = a.NS;
     uint8_t* const me = a.peers.win[a.rank];
     uint8_t* const them = a.peers.win[p];
+    // role of this CTA and the byte range [lo, hi) of the chunk it works on
+    int role = a.variant, nct = a.ctas_per_peer;
+    uint64_t lo = 0, hi = S;
+    if (a.variant == B200PROBE_A2A_MIX_TMA) {
+        if (sub < a.push_ctas) { role = B200PROBE_A2A_PUSH_TMA; nct = a.push_ctas; hi = a.split; }
+        else { role = B200PROBE_A2A_PULL_TMA; sub -= a.push_ctas; nct = a.ctas_per_peer - a.push_ctas; lo = a.split; }
+        if (p == a.rank) {                              // local slot (only_peer == -1): one role writes all of it
+            const bool mine = a.push_ctas > 0 ? role == B200PROBE_A2A_PUSH_TMA : true;
+            lo = 0; hi = mine ? S : 0;
+        }
+    }
     const uint8_t* in;
     uint8_t* out;
-    if (a.variant == B200PROBE_A2A_PULL_TMA) {          // their send[rank] -> my recv[p]
+    if (role == B200PROBE_A2A_PULL_TMA) {               // their send[rank] -> my recv[p]
         in = them + ((uint64_t)a.world + a.rank) * S;
         out = me + (uint64_t)p * S;
     } else {                                            // (my send[p] | generated) -> their recv[rank]
         in = me + ((uint64_t)a.world + p) * S;
         out = them + (uint64_t)a.rank * S;
     }
-    const uint64_t nchunks = (S + SB - 1) / SB;
-    const uint64_t worker = (uint64_t)sub * kRingWarps + warp, nworkers = (uint64_t)a.ctas_per_peer * kRingWarps;
+    const uint64_t nchunks = hi > lo ? (hi - lo + SB - 1) / SB : 0;
+    const uint64_t worker = (uint64_t)sub * kRingWarps + warp, nworkers = (uint64_t)nct * kRingWarps;
     const uint64_t n_my = worker < nchunks ? (nchunks - worker + nworkers - 1) / nworkers : 0;
     const uint32_t ring = smem_u32(smem) + warp * NS * SB;
     uint8_t* ring_ptr = smem + (size_t)warp * NS * SB;
     const uint32_t bar0 = smem_u32(&full_bar[warp * kRingMaxStages]);
     const uint64_t pol = policy_evict_first();
-    auto off_of = [&](uint64_t k) { return (worker + k * nworkers) * (uint64_t)SB; };
-    auto len_of = [&](uint64_t k) { return (uint32_t)min((uint64_t)SB, S - off_of(k)); };
+    auto off_of = [&](uint64_t k) { return lo + (worker + k * nworkers) * (uint64_t)SB; };
+    auto len_of = [&](uint64_t k) { return (uint32_t)min((uint64_t)SB, hi - off_of(k)); };
     uint32_t cs = 0, cph = 0;
-    if (a.variant != B200PROBE_A2A_PUSH_TMA) {
+    if (role != B200PROBE_A2A_PUSH_TMA) {
         if (lane == 0 && n_my > 0) {       // bulk load -> bulk store; the data never touches registers
             uint64_t issued = 0;
             uint32_t ps = 0;
@@ -172,8 +188,9 @@ int launch_exchange(int ordinal, int rank, int world, void* const* windows, uint
                     int only_peer, cudaStream_t stream) {
     if (world < 1 || world > kMaxWorld || rank < 0 || rank >= world || !windows) { b200::set_error("a2a: bad rank/world"); return B200PROBE_EINVAL; }
     if (S & 15) { b200::set_error("a2a: bytes_per_pair must be a multiple of 16"); return B200PROBE_EINVAL; }
-    if (variant < 0 || variant > B200PROBE_A2A_PUSH_BUF) { b200::set_error("a2a: unknown variant %d", variant); return B200PROBE_EINVAL; }
+    if (variant < 0 || variant > B200PROBE_A2A_MIX_TMA) { b200::set_error("a2a: unknown variant %d", variant); return B200PROBE_EINVAL; }
     if (variant == B200PROBE_A2A_AUTO) variant = only_peer >= 0 ? B200PROBE_A2A_PULL_TMA : B200PROBE_A2A_PUSH_TMA;
+    if (variant == B200PROBE_A2A_MIX_TMA && only_peer >= 0) variant = B200PROBE_A2A_PULL_TMA;   // one direction at a time: nothing to mix
     if (only_peer >= world) { b200::set_error("a2a: peer %d out of range", only_peer); return B200PROBE_ERANGE; }
     b200::DevProps props;
     int rc = b200::device_props(ordinal, &props);
@@ -192,6 +209,18 @@ int launch_exchange(int ordinal, int rank, int world, void* const* windows, uint
         // about one CTA per SM in total, split over the peers; 4 warps x 4 stages x 8 KiB = 128 KiB per CTA
         a.ctas_per_peer = ctas_per_peer > 0 ? ctas_per_peer : std::max(1, props.sms / targets);
         a.SB = 8192; a.NS = 4;
+        if (const char* e = getenv("B200PROBE_A2A_STAGE_BYTES")) { int v = atoi(e); if (v >= 512 && v <= 49152 && !(v & 511)) a.SB = (uint32_t)v; }
+        if (const char* e = getenv("B200PROBE_A2A_STAGES")) { int v = atoi(e); if (v >= 2 && v <= kRingMaxStages) a.NS = (uint32_t)v; }
+        if ((size_t)kRingWarps * a.NS * a.SB > 200u * 1024u) { b200::set_error("a2a: ring of %u x %u B stages does not fit shared memory", a.NS, a.SB); return B200PROBE_EINVAL; }
+        if (variant == B200PROBE_A2A_MIX_TMA) {
+            int pct = 50;
+            if (const char* e = getenv("B200PROBE_A2A_MIX_PCT")) pct = std::min(100, std::max(0, atoi(e)));
+            const uint64_t stages_total = (S + a.SB - 1) / a.SB;
+            a.split = std::min<uint64_t>(S, (stages_total * pct / 100) * a.SB);
+            if (a.ctas_per_peer < 2) a.ctas_per_peer = 2;
+            a.push_ctas = a.split == 0 ? 0 : a.split == S ? a.ctas_per_peer
+                                                          : std::min(a.ctas_per_peer - 1, std::max(1, (int)((int64_t)a.ctas_per_peer * pct / 100)));
+        }
         const size_t smem = (size_t)kRingWarps * a.NS * a.SB;
         B200_CUDA_TRY(cudaFuncSetAttribute(a2a_ring_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         a2a_ring_kernel<<<world * a.ctas_per_peer, kRingWarps * 32, smem, stream>>>(a);
@@ -368,7 +397,9 @@ int b200probe_nvlink_a2a(const int* ordinals, int g, const b200probe_a2a_cfg_t* 
     if (pair_gbs) std::fill(pair_gbs, pair_gbs + g * g, 0.0);
     const bool nccl_mode = cfg.mode == B200PROBE_A2A_NCCL;
     if (cfg.variant == B200PROBE_A2A_AUTO) cfg.variant = cfg.mode == B200PROBE_A2A_PEER_PAIR ? B200PROBE_A2A_PULL_TMA : B200PROBE_A2A_PUSH_TMA;
+    if (cfg.variant == B200PROBE_A2A_MIX_TMA && cfg.mode == B200PROBE_A2A_PEER_PAIR) cfg.variant = B200PROBE_A2A_PULL_TMA;
     const bool pull = !nccl_mode && cfg.variant == B200PROBE_A2A_PULL_TMA;
+    const bool mix = !nccl_mode && cfg.variant == B200PROBE_A2A_MIX_TMA;
 
     int rc = b200probe_enable_peer_access(ordinals, g);
     if (rc) return rc;
@@ -498,8 +529,8 @@ int b200probe_nvlink_a2a(const int* ordinals, int g, const b200probe_a2a_cfg_t* 
         for (int i = 0; i < g; ++i) {
             const double own = payload / (median_of(per_dev[i]) * 1e-3) / 1e9;      // the direction rank i's kernel drives
             const double common = payload / (out->ms_median * 1e-3) / 1e9;          // the other direction, over the common window
-            out->egress_gbs[i] = pull ? common : own;
-            out->ingress_gbs[i] = pull ? own : common;
+            out->egress_gbs[i] = mix ? own : pull ? common : own;       // MIX: rank i's kernel drives half of either direction
+            out->ingress_gbs[i] = mix ? own : pull ? own : common;
             for (int j = 0; j < g; ++j) {
                 if (i == j) continue;
                 const double gbs = own / (g - 1);                                   // per-pair share under full concurrency

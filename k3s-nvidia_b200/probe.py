@@ -215,6 +215,22 @@ class Probe:
                     "hbm_copy_host")
         return s64.value, x32.value
 
+    def host_alloc(self, nbytes: int):
+        """Pinned host buffer as a numpy uint8 array (free with host_free(arr))."""
+        import numpy as np
+
+        ptr = C.c_void_p()
+        self._check(self.lib.b200probe_host_alloc(nbytes, C.byref(ptr)), "host_alloc")
+        arr = np.ctypeslib.as_array((C.c_uint8 * nbytes).from_address(ptr.value))
+        self._pinned = getattr(self, "_pinned", {})
+        self._pinned[arr.ctypes.data] = ptr.value
+        return arr
+
+    def host_free(self, arr) -> None:
+        ptr = getattr(self, "_pinned", {}).pop(arr.ctypes.data, None)
+        if ptr is not None:
+            self._check(self.lib.b200probe_host_free(ptr), "host_free")
+
     # -- NVLink ----------------------------------------------------------------------------------
     def nvlink_a2a(self, ordinals: Sequence[int], *, bytes_per_pair=None, mode=L.A2A_PEER_ALL, warmup=None, reps=None,
                    seed=0xB200, verify=1, ctas_per_peer=None, variant=L.A2A_AUTO) -> A2aReport:

@@ -23,7 +23,7 @@ def env():
     return torch, Probe(), _oracle.load()
 
 
-VARIANTS = {0: "auto", 1: "pull-tma", 2: "push-tma", 3: "push-direct", 4: "push-buf"}
+VARIANTS = {0: "auto", 1: "pull-tma", 2: "push-tma", 3: "push-direct", 4: "push-buf", 5: "mix-tma"}
 
 
 @pytest.mark.parametrize("S", [16, 4096 + 16, 1 << 20, (3 << 20) + 48])

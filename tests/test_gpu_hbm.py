@@ -74,6 +74,30 @@ def test_copy_host_roundtrip(env):
     assert (s, x) == _oracle.checksum(o, src)
 
 
+def test_copy_host_roundtrip_pinned_pipelined(env):
+    """Pinned buffers through the three-stream chunk pipeline (ragged last chunk, several chunk sizes)."""
+    import os
+
+    torch, p, o = env
+    nbytes = (40 << 20) + 20
+    src = p.host_alloc(nbytes)
+    dst = p.host_alloc(nbytes)
+    try:
+        rng = np.random.default_rng(5)
+        src[:] = rng.integers(0, 256, size=nbytes, dtype=np.uint8)
+        for chunk in (None, 1 << 20, (3 << 20) + 16):
+            if chunk:
+                os.environ["B200PROBE_HOST_CHUNK_BYTES"] = str(chunk)
+            dst[:] = 0
+            s, x = p.hbm_copy_host(0, src, dst)
+            os.environ.pop("B200PROBE_HOST_CHUNK_BYTES", None)
+            assert np.array_equal(src, dst)
+            assert (s, x) == _oracle.checksum(o, src.view(np.uint32))
+    finally:
+        p.host_free(src)
+        p.host_free(dst)
+
+
 def test_full_size_properties(env):
     """BASELINE config 2 at its largest size (1 GiB): closed-form checksum of the pattern,
     copy == source (checksum of checksums), idempotence of a second copy."""
