@@ -24,12 +24,13 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+os.environ["NCCL_DEBUG"] = os.environ.get("B200PROBE_NCCL_DEBUG", "WARN")   # NCCL_DEBUG=VERSION prints a banner on stdout; stdout carries ONE JSON line
 
 GIB = 1 << 30
 METRIC = "health-probe HBM GB/s & NVLink GB/s vs peak per GPU at 1/2/4/8 B200"
 WORKLOAD = "configs[1]: single-B200 HBM bandwidth probe, copy pass at the 1 GiB verdict size of the 1 MiB-1 GiB sweep"
 NVLINK_NOMINAL = 900.0
-A2A_VARIANT = int(os.environ.get("B200PROBE_A2A_VARIANT", "0"))   # 0 AUTO (= PUSH_TMA for the exchange), 1 PULL_TMA, 2 PUSH_TMA, 3 PUSH_DIRECT, 4 PUSH_BUF
+A2A_VARIANT = int(os.environ.get("B200PROBE_A2A_VARIANT", "0"))   # 0 AUTO (= PUSH_SYNC for the exchange), 1 PULL_TMA, 2 PUSH_TMA, 3 PUSH_DIRECT, 4 PUSH_BUF, 5 MIX_TMA, 6 PUSH_STAGGER, 7 PUSH_SYNC
 NVLINK_MEASURED = 770.0   # /opt/skills/guides/B200_PROFILING.md, peer copy per direction
 
 
@@ -332,7 +333,8 @@ def run_ours(args):
 def nvlink_exchange(torch, D, p, local_rank, rank, world, stream, args):
     """configs[2]: every rank owns a window [recv world x S][send world x S]; handles are exchanged
     over torch.distributed (control data only) and every rank PUSHES its chunks into its peers' recv
-    slots over NVLink with our TMA kernel (pushes beat pulls when both directions are loaded); device-timed, max over ranks; landed data verified."""
+    slots over NVLink with our TMA kernel (pushes beat pulls when both directions are loaded), one peer
+    per step with a device-side step barrier; device-timed, max over ranks; landed data verified."""
     S = 256 << 20
     lib = p.lib
     seed = 0xB200
@@ -395,7 +397,9 @@ def nvlink_exchange(torch, D, p, local_rank, rank, world, stream, args):
     lib.b200probe_a2a_window_release(local_rank, win, 0)
     per_dir = (world - 1) * S / (ms * 1e-3) / 1e9
     push = "a2a_ring_kernel PUSH_TMA (pattern in smem, cp.async.bulk stores into IPC peer-mapped windows)"
-    names = {0: push, 1: "a2a_ring_kernel PULL_TMA (cp.async.bulk loads from IPC peer-mapped windows, bulk stores to local HBM)", 2: push,
+    sync = ("a2a_stagger_kernel PUSH_SYNC (pattern in smem, cp.async.bulk stores into IPC peer-mapped windows; peers visited one at a "
+            "time, rank r -> (r+t) mod G, with a device-side barrier over NVLink flags before every step)")
+    names = {0: sync if world > 2 else push, 7: sync, 6: "a2a_stagger_kernel PUSH_STAGGER (no step barrier)", 5: "a2a_ring_kernel MIX_TMA", 1: "a2a_ring_kernel PULL_TMA (cp.async.bulk loads from IPC peer-mapped windows, bulk stores to local HBM)", 2: push,
              3: "a2a_direct_kernel PUSH_DIRECT (16-byte stores on peer pointers)", 4: "a2a_ring_kernel PUSH_BUF"}
     return {"bytes_per_pair": S, "ms_per_exchange": round(ms, 4), "gbs_per_gpu_per_direction": round(per_dir, 1),
             "aggregate_gbs": round(per_dir * world, 1), "frac_of_nominal_900": round(per_dir / NVLINK_NOMINAL, 4),

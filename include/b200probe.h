@@ -194,7 +194,8 @@ int b200probe_host_free(void* ptr);
 #define B200PROBE_A2A_PEER_PAIR   1   /* same kernel, one (src,dst) pair at a time -> matrix       */
 #define B200PROBE_A2A_NCCL        2   /* grouped ncclSend/ncclRecv (the library leg, for contrast) */
 /* exchange kernels (cfg.variant) */
-#define B200PROBE_A2A_AUTO        0   /* PUSH_TMA for the concurrent exchange, PULL_TMA for one pair */
+#define B200PROBE_A2A_AUTO        0   /* one pair: PULL_TMA; concurrent exchange: PUSH_SYNC when G > 2 and
+                                         S >= 64 MiB (the barrier must outweigh launch skew), else PUSH_TMA */
 #define B200PROBE_A2A_PULL_TMA    1   /* bulk-LOAD the peers' send chunks over NVLink: best one-way
                                          (756-781 GB/s), worse when both directions are loaded (626) */
 #define B200PROBE_A2A_PUSH_TMA    2   /* generate in shared memory, bulk-STORE into the peers: best
@@ -203,6 +204,13 @@ int b200probe_host_free(void* ptr);
 #define B200PROBE_A2A_PUSH_BUF    4   /* bulk-load the local send chunk, bulk-store into the peer   */
 #define B200PROBE_A2A_MIX_TMA     5   /* each chunk moved from both ends: head pushed by its source,
                                          tail pulled by its destination ($B200PROBE_A2A_MIX_PCT)     */
+
+#define B200PROBE_A2A_PUSH_STAGGER 6  /* PUSH_TMA with the peers visited one at a time, rank r sending to
+                                         (r+t) mod G at step t: one source per destination at a time */
+
+#define B200PROBE_A2A_PUSH_SYNC    7  /* PUSH_STAGGER + a device-side barrier over all ranks before every
+                                         step (flags in the windows' sync pages, written over NVLink):
+                                         687 GB/s per direction at G = 8 vs 640-660 unsynchronised    */
 
 typedef struct b200probe_a2a_cfg {
     uint64_t bytes_per_pair;        /* S, multiple of 16; 0 = 256 MiB                              */
@@ -232,11 +240,14 @@ int b200probe_nvlink_a2a(const int* cuda_ordinals, int g, const b200probe_a2a_cf
 int b200probe_enable_peer_access(const int* cuda_ordinals, int g);
 
 /* Building blocks (one process per GPU under torchrun, or a host that owns its windows).
- * Window layout on every rank:  [recv: world x S][send: world x S]  bytes;
- *   send[p] = this rank's chunk for rank p, recv[p] = where rank p's chunk lands.
+ * Window layout on every rank:  [recv: world x S][send: world x S][sync page]  bytes;
+ *   send[p] = this rank's chunk for rank p, recv[p] = where rank p's chunk lands; the sync page
+ *   (B200PROBE_A2A_SYNC_BYTES, zeroed at creation) holds the step-barrier flags of PUSH_SYNC.  A caller
+ *   that allocates its own windows must provide 2*world*S + B200PROBE_A2A_SYNC_BYTES bytes and zero the page.
  * create -> (export the 64-byte IPC handle, exchange by any transport, import the peers') ->
  * fill -> exchange.  */
 #define B200PROBE_IPC_HANDLE_BYTES 64
+#define B200PROBE_A2A_SYNC_BYTES   4096
 int b200probe_a2a_window_create(int cuda_ordinal, int world, uint64_t bytes_per_pair,
                                 void** window, unsigned char* ipc_handle_out);
 int b200probe_a2a_window_fill(int cuda_ordinal, void* window, int rank, int world,

@@ -17,7 +17,8 @@ IPC_HANDLE_BYTES = 64
 HBM_READ, HBM_WRITE, HBM_COPY = 1, 2, 4
 VARIANT_TMA, VARIANT_DIRECT = 0, 1
 A2A_PEER_ALL, A2A_PEER_PAIR, A2A_NCCL = 0, 1, 2
-A2A_AUTO, A2A_PULL_TMA, A2A_PUSH_TMA, A2A_PUSH_DIRECT, A2A_PUSH_BUF, A2A_MIX_TMA = 0, 1, 2, 3, 4, 5
+A2A_AUTO, A2A_PULL_TMA, A2A_PUSH_TMA, A2A_PUSH_DIRECT, A2A_PUSH_BUF, A2A_MIX_TMA, A2A_PUSH_STAGGER, A2A_PUSH_SYNC = 0, 1, 2, 3, 4, 5, 6, 7
+A2A_SYNC_BYTES = 4096
 NVML_ERROR_TIMEOUT = 10
 EVENT_XID_CRITICAL = 0x8
 EVENT_DBE = 0x2

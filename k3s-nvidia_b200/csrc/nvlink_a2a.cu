@@ -1,6 +1,6 @@
 // NVLink 5 all-to-all probe (no reference counterpart).
 //
-// Every rank owns one window in HBM:  [recv: world x S bytes][send: world x S bytes]
+// Every rank owns one window in HBM:  [recv: world x S bytes][send: world x S bytes][sync page: 4 KiB]
 //   send[p] = the chunk this rank has for rank p   (pattern under chunk_seed(seed, rank, p))
 //   recv[p] = where rank p's chunk for this rank lands
 // Windows are peer-mapped (cudaDeviceEnablePeerAccess in one process, cudaIpc* across processes)
@@ -11,9 +11,15 @@
 //   PULL_TMA    each rank bulk-LOADS its peers' send chunks over NVLink into shared memory and
 //               bulk-stores them into its own recv slots.  Best for ONE direction at a time (the
 //               pairwise matrix): 756-781 GB/s vs 699-712 for writes (profiles/p2p_pull_tune_r01.txt)
-//   AUTO        (default) PUSH_TMA for the concurrent exchange, PULL_TMA for an isolated pair
+//   AUTO        (default) PULL_TMA for an isolated pair; for the concurrent exchange PUSH_SYNC when G > 2
+//               and S >= 64 MiB, else PUSH_TMA
 //   PUSH_DIRECT pattern generated in registers, 16-byte stores on the peer pointers
 //   PUSH_BUF    local send chunk bulk-loaded, bulk-stored to the peer
+//   PUSH_STAGGER PUSH_TMA, but the whole grid works on one peer at a time in the rotation (rank+t) mod G
+//   PUSH_SYNC   PUSH_STAGGER with a device-side barrier across ALL ranks before every step (flags in the
+//               4 KiB sync page that ends each window, written over NVLink): steps stay aligned, so every
+//               GPU sends to one peer and receives from one peer at any time.  687 GB/s per direction at
+//               G = 8 against 640-660 for the concurrent push (profiles/a2a_step_sync_r01_g8.txt)
 //   MIX_TMA     every (src,dst) chunk is moved by BOTH ends at once: the first `split` bytes are pushed
 //               by src (PUSH_TMA), the rest pulled by dst (PULL_TMA), so each link direction carries
 //               posted writes and read responses side by side (B200PROBE_A2A_MIX_PCT = pushed share)
@@ -53,7 +59,19 @@ struct XArgs {
     uint32_t SB, NS;   // ring stage bytes / stages
     uint64_t split;    // MIX_TMA: bytes [0,split) of every chunk are pushed by its source, [split,S) pulled by its destination
     int push_ctas;     // MIX_TMA: CTAs (of ctas_per_peer) in the push role
+    uint32_t timeout_us;   // PUSH_SYNC: longest wait at a step barrier before the launch gives up synchronising
 };
+
+// Sync page at window + 2*world*S (zeroed when the window is created).  flag[q] is written by rank q with a
+// remote store over NVLink; cnt and epoch are local.  epoch counts the synchronised launches on this
+// window: every rank runs the same sequence of exchanges, so the epochs agree without being communicated,
+// and a rank that is behind only makes its peers wait out the barrier timeout (never a hang).
+struct SyncPage {
+    uint32_t flag[kMaxWorld];
+    uint32_t cnt;
+    uint32_t epoch;
+};
+static_assert(sizeof(SyncPage) <= B200PROBE_A2A_SYNC_BYTES, "sync page");
 
 __device__ __forceinline__ bool cta_peer(const XArgs& a, int* peer, int* sub) {
     const int p = blockIdx.x / a.ctas_per_peer;
@@ -158,6 +176,96 @@ __global__ void __launch_bounds__(kRingWarps * 32) a2a_ring_kernel(XArgs a) {
     }
 }
 
+// ---- staggered push: the whole grid visits the peers ONE AT A TIME in the rotation (rank+t) mod world,
+// so at any moment every GPU receives from a single source (no output-port sharing inside NVSwitch).
+// Same data path as PUSH_TMA (pattern -> shared memory -> bulk store); the ring of stages runs on
+// across peers without draining.
+__global__ void __launch_bounds__(kRingWarps * 32) a2a_stagger_kernel(XArgs a) {
+    using namespace b200ptx;
+    extern __shared__ __align__(128) uint8_t smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint64_t S = a.S;
+    const uint32_t SB = a.SB, NS = a.NS;
+    const uint64_t nchunks = (S + SB - 1) / SB;
+    const uint64_t worker = (uint64_t)blockIdx.x * kRingWarps + warp, nworkers = (uint64_t)gridDim.x * kRingWarps;
+    const uint64_t n_my = worker < nchunks ? (nchunks - worker + nworkers - 1) / nworkers : 0;
+    const uint32_t ring = smem_u32(smem) + warp * NS * SB;
+    uint8_t* ring_ptr = smem + (size_t)warp * NS * SB;
+    const uint64_t pol = policy_evict_first();
+    uint32_t cs = 0;
+    uint64_t stored = 0;
+    const bool sync = a.variant == B200PROBE_A2A_PUSH_SYNC && a.only_peer < 0;
+    __shared__ int s_desync;
+    if (threadIdx.x == 0) s_desync = 0;
+    SyncPage* const mine = reinterpret_cast<SyncPage*>(a.peers.win[a.rank] + 2ull * a.world * S);
+    uint32_t epoch = 0;
+    if (sync) asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(epoch) : "l"(&mine->epoch) : "memory");   // bumped only after every CTA's last arrival
+    for (int t = (a.only_peer == -1 ? 0 : 1); t < a.world; ++t) {
+        const int p = (a.rank + t) % a.world;
+        if (a.only_peer >= 0 && p != a.only_peer) continue;
+        if (sync && t >= 1) {
+            // ---- barrier t-1 over every CTA of every rank: arrive locally, last arriver raises this rank's
+            // flag on all ranks, then everyone polls its LOCAL sync page.  A wait longer than timeout_us gives
+            // up synchronising for the rest of the launch (a peer that never launched must not hang the GPU).
+            const uint32_t b = (uint32_t)(t - 1), nb = (uint32_t)(a.world - 1);
+            const uint32_t target = epoch * 16u + b + 1u;
+            __syncthreads();                    // every warp of this CTA has issued its stores of the step before
+            if (threadIdx.x == 0) {
+                const uint32_t n = atomicAdd(&mine->cnt, 1u);
+                if (n == gridDim.x * (b + 1) - 1) {
+                    if (b + 1 == nb) { atomicExch(&mine->cnt, 0u); atomicExch(&mine->epoch, epoch + 1u); }   // last barrier of the launch
+                    for (int q = 0; q < a.world; ++q) {
+                        SyncPage* theirs = reinterpret_cast<SyncPage*>(a.peers.win[q] + 2ull * a.world * S);
+                        asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(&theirs->flag[a.rank]), "r"(target) : "memory");
+                    }
+                }
+            }
+            if (warp == 0 && !s_desync) {
+                uint64_t t0, now;
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+                bool ok = false;
+                while (!ok) {
+                    uint32_t v = target;
+                    if (lane < a.world) asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(&mine->flag[lane]) : "memory");
+                    ok = __all_sync(0xffffffffu, (int32_t)(v - target) >= 0);
+                    if (!ok) {
+                        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+                        if (__any_sync(0xffffffffu, now - t0 > (uint64_t)a.timeout_us * 1000ull)) {      // warp-uniform decision
+                            if (lane == 0) s_desync = 1;
+                            break;
+                        }
+                        __nanosleep(200);
+                    }
+                }
+            }
+            __syncthreads();
+        }
+        uint8_t* const out = a.peers.win[p] + (uint64_t)a.rank * S;
+        const uint32_t sd = chunk_seed(a.seed, a.rank, p);
+        for (uint64_t k = 0; k < n_my; ++k, ++stored) {
+            const uint64_t off = (worker + k * nworkers) * (uint64_t)SB;
+            const uint32_t len = (uint32_t)min((uint64_t)SB, S - off);
+            if (stored >= NS) {
+                if (lane == 0) bulk_wait_read_dyn((int)NS - 1);
+                __syncwarp();
+            }
+            uint4* st = reinterpret_cast<uint4*>(ring_ptr + (size_t)cs * SB);
+            const uint32_t nvec = len >> 4;
+            const uint64_t w0 = off >> 2;
+#pragma unroll 4
+            for (uint32_t i = lane; i < nvec; i += 32) {
+                const uint64_t w = w0 + (uint64_t)i * 4;
+                st[i] = make_uint4(b200_pattern_word(w, sd), b200_pattern_word(w + 1, sd), b200_pattern_word(w + 2, sd), b200_pattern_word(w + 3, sd));
+            }
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) { bulk_s2g(out + off, ring + cs * SB, len, pol); bulk_commit(); }
+            if (++cs == NS) cs = 0;
+        }
+    }
+    if (lane == 0) bulk_wait_all();
+}
+
 // ---- direct push: pattern in registers, 16-byte stores on the peer pointer --------------------------
 __global__ void __launch_bounds__(512) a2a_direct_kernel(XArgs a) {
     int p, sub;
@@ -184,12 +292,19 @@ __global__ void __launch_bounds__(512) a2a_direct_kernel(XArgs a) {
     }
 }
 
+// AUTO for the concurrent exchange.  The step barrier pays once a step is much longer than the launch skew
+// between ranks (tens of microseconds): at G = 8, S = 256 MiB it lifts 640-660 GB/s to 680; at S = 16 MiB
+// it costs 40 % (profiles/a2a_sync_r01_g8.txt).  With two ranks there is one peer and nothing to stagger.
+int auto_exchange_variant(int world, uint64_t S) {
+    return (world > 2 && S >= (64ull << 20)) ? B200PROBE_A2A_PUSH_SYNC : B200PROBE_A2A_PUSH_TMA;
+}
+
 int launch_exchange(int ordinal, int rank, int world, void* const* windows, uint64_t S, uint32_t seed, int variant, int ctas_per_peer,
                     int only_peer, cudaStream_t stream) {
     if (world < 1 || world > kMaxWorld || rank < 0 || rank >= world || !windows) { b200::set_error("a2a: bad rank/world"); return B200PROBE_EINVAL; }
     if (S & 15) { b200::set_error("a2a: bytes_per_pair must be a multiple of 16"); return B200PROBE_EINVAL; }
-    if (variant < 0 || variant > B200PROBE_A2A_MIX_TMA) { b200::set_error("a2a: unknown variant %d", variant); return B200PROBE_EINVAL; }
-    if (variant == B200PROBE_A2A_AUTO) variant = only_peer >= 0 ? B200PROBE_A2A_PULL_TMA : B200PROBE_A2A_PUSH_TMA;
+    if (variant < 0 || variant > B200PROBE_A2A_PUSH_SYNC) { b200::set_error("a2a: unknown variant %d", variant); return B200PROBE_EINVAL; }
+    if (variant == B200PROBE_A2A_AUTO) variant = only_peer >= 0 ? B200PROBE_A2A_PULL_TMA : auto_exchange_variant(world, S);
     if (variant == B200PROBE_A2A_MIX_TMA && only_peer >= 0) variant = B200PROBE_A2A_PULL_TMA;   // one direction at a time: nothing to mix
     if (only_peer >= world) { b200::set_error("a2a: peer %d out of range", only_peer); return B200PROBE_ERANGE; }
     b200::DevProps props;
@@ -222,8 +337,19 @@ int launch_exchange(int ordinal, int rank, int world, void* const* windows, uint
                                                           : std::min(a.ctas_per_peer - 1, std::max(1, (int)((int64_t)a.ctas_per_peer * pct / 100)));
         }
         const size_t smem = (size_t)kRingWarps * a.NS * a.SB;
-        B200_CUDA_TRY(cudaFuncSetAttribute(a2a_ring_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        a2a_ring_kernel<<<world * a.ctas_per_peer, kRingWarps * 32, smem, stream>>>(a);
+        if (variant == B200PROBE_A2A_PUSH_STAGGER || variant == B200PROBE_A2A_PUSH_SYNC) {
+            int grid = ctas_per_peer > 0 ? ctas_per_peer : props.sms;            // here: CTAs in total, all on one peer at a time
+            if (variant == B200PROBE_A2A_PUSH_SYNC) {
+                grid = std::min(grid, props.sms);                                // the barrier needs every CTA resident (1 CTA/SM at this ring size)
+                a.timeout_us = 200000;
+                if (const char* e = getenv("B200PROBE_A2A_SYNC_TIMEOUT_US")) { int v = atoi(e); if (v > 0) a.timeout_us = (uint32_t)v; }
+            }
+            B200_CUDA_TRY(cudaFuncSetAttribute(a2a_stagger_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            a2a_stagger_kernel<<<grid, kRingWarps * 32, smem, stream>>>(a);
+        } else {
+            B200_CUDA_TRY(cudaFuncSetAttribute(a2a_ring_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            a2a_ring_kernel<<<world * a.ctas_per_peer, kRingWarps * 32, smem, stream>>>(a);
+        }
     }
     B200_CUDA_TRY(cudaGetLastError());
     return 0;
@@ -334,7 +460,7 @@ int b200probe_a2a_window_create(int ordinal, int world, uint64_t S, void** windo
     if (rc) return rc;
     B200_CUDA_TRY(cudaSetDevice(ordinal));
     void* p = nullptr;
-    const uint64_t bytes = std::max<uint64_t>(16, 2ull * world * S);
+    const uint64_t bytes = 2ull * world * S + B200PROBE_A2A_SYNC_BYTES;
     B200_CUDA_TRY(cudaMalloc(&p, bytes));
     B200_CUDA_TRY(cudaMemset(p, 0, bytes));
     if (handle_out) {
@@ -396,7 +522,7 @@ int b200probe_nvlink_a2a(const int* ordinals, int g, const b200probe_a2a_cfg_t* 
     out->verified = -1;
     if (pair_gbs) std::fill(pair_gbs, pair_gbs + g * g, 0.0);
     const bool nccl_mode = cfg.mode == B200PROBE_A2A_NCCL;
-    if (cfg.variant == B200PROBE_A2A_AUTO) cfg.variant = cfg.mode == B200PROBE_A2A_PEER_PAIR ? B200PROBE_A2A_PULL_TMA : B200PROBE_A2A_PUSH_TMA;
+    if (cfg.variant == B200PROBE_A2A_AUTO) cfg.variant = cfg.mode == B200PROBE_A2A_PEER_PAIR ? B200PROBE_A2A_PULL_TMA : auto_exchange_variant(g, cfg.bytes_per_pair);
     if (cfg.variant == B200PROBE_A2A_MIX_TMA && cfg.mode == B200PROBE_A2A_PEER_PAIR) cfg.variant = B200PROBE_A2A_PULL_TMA;
     const bool pull = !nccl_mode && cfg.variant == B200PROBE_A2A_PULL_TMA;
     const bool mix = !nccl_mode && cfg.variant == B200PROBE_A2A_MIX_TMA;
@@ -412,8 +538,9 @@ int b200probe_nvlink_a2a(const int* ordinals, int g, const b200probe_a2a_cfg_t* 
         B200_CUDA_TRY(cudaStreamCreateWithFlags(&p.stream, cudaStreamNonBlocking));
         B200_CUDA_TRY(cudaEventCreate(&p.e0));
         B200_CUDA_TRY(cudaEventCreate(&p.e1));
-        B200_CUDA_TRY(cudaMalloc(&p.window, 2ull * g * S));
+        B200_CUDA_TRY(cudaMalloc(&p.window, 2ull * g * S + B200PROBE_A2A_SYNC_BYTES));
         B200_CUDA_TRY(cudaMemsetAsync(p.window, 0, (size_t)g * S, p.stream));
+        B200_CUDA_TRY(cudaMemsetAsync(p.window + 2ull * g * S, 0, B200PROBE_A2A_SYNC_BYTES, p.stream));
         B200_CUDA_TRY(cudaMalloc(&p.partials, 32));
         rc = fill_send_half(p.ordinal, p.window, i, g, S, cfg.seed, p.stream);
         if (rc) return rc;

@@ -23,7 +23,8 @@ def env():
     return torch, Probe(), _oracle.load()
 
 
-VARIANTS = {0: "auto", 1: "pull-tma", 2: "push-tma", 3: "push-direct", 4: "push-buf", 5: "mix-tma"}
+VARIANTS = {0: "auto", 1: "pull-tma", 2: "push-tma", 3: "push-direct", 4: "push-buf", 5: "mix-tma", 6: "push-stagger", 7: "push-sync"}
+SYNC = 4096      # B200PROBE_A2A_SYNC_BYTES: the step-barrier page that ends every window
 
 
 @pytest.mark.parametrize("S", [16, 4096 + 16, 1 << 20, (3 << 20) + 48])
@@ -33,8 +34,10 @@ def test_exchange_lands_oracle_pattern_in_every_recv_slot(env, S, variant):
     g = min(torch.cuda.device_count(), 8)
     ords = (C.c_int * g)(*range(g))
     p._check(p.lib.b200probe_enable_peer_access(ords, g), "enable_peer_access")
-    # windows owned by the test (torch tensors): [recv g x S][send g x S] + guard bytes
-    wins = [torch.full((2 * g * S + 64,), 0x5A, dtype=torch.uint8, device=f"cuda:{r}") for r in range(g)]
+    # windows owned by the test (torch tensors): [recv g x S][send g x S][sync page, zeroed] + guard bytes
+    wins = [torch.full((2 * g * S + SYNC + 64,), 0x5A, dtype=torch.uint8, device=f"cuda:{r}") for r in range(g)]
+    for w in wins:
+        w[2 * g * S:2 * g * S + SYNC] = 0
     peers = (C.c_void_p * g)(*[w.data_ptr() for w in wins])
     for r in range(g):
         st = torch.cuda.current_stream(r).cuda_stream
@@ -54,7 +57,8 @@ def test_exchange_lands_oracle_pattern_in_every_recv_slot(env, S, variant):
         torch.cuda.synchronize(r)
     for dst in range(g):
         host = wins[dst].cpu().numpy()
-        assert (host[2 * g * S:] == 0x5A).all(), "wrote past the window"
+        assert (host[2 * g * S + SYNC:] == 0x5A).all(), "wrote past the window"
+        assert not host[2 * g * S + 72:2 * g * S + SYNC].any(), "sync page: only flag[16], cnt, epoch may change"
         for src in range(g):
             want = _oracle.pattern(o, 0, S // 4, o.oracle_a2a_chunk_seed(SEED, src, dst))
             got = host[src * S:(src + 1) * S].view(np.uint32)
@@ -68,7 +72,7 @@ def test_only_peer_selectors(env):
     S = 1 << 16
     ords = (C.c_int * g)(*range(g))
     p._check(p.lib.b200probe_enable_peer_access(ords, g), "enable_peer_access")
-    wins = [torch.zeros(2 * g * S, dtype=torch.uint8, device=f"cuda:{r}") for r in range(g)]
+    wins = [torch.zeros(2 * g * S + SYNC, dtype=torch.uint8, device=f"cuda:{r}") for r in range(g)]
     peers = (C.c_void_p * g)(*[w.data_ptr() for w in wins])
     for r in range(g):
         p._check(p.lib.b200probe_a2a_window_fill(r, wins[r].data_ptr(), r, g, S, SEED, torch.cuda.current_stream(r).cuda_stream), "fill")
@@ -76,7 +80,8 @@ def test_only_peer_selectors(env):
     st0 = torch.cuda.current_stream(0).cuda_stream
     p._check(p.lib.b200probe_a2a_exchange(0, 0, g, peers, S, SEED, 0, 0, -2, st0), "exchange -2")     # peers only
     torch.cuda.synchronize(0)
-    # AUTO + all peers = PUSH_TMA: rank 0 writes its chunks into every PEER's recv[0] slot only
+    # AUTO + all peers = PUSH_SYNC; with no peer launched the step barrier times out (200 ms) and the
+    # launch carries on unsynchronised: rank 0 writes its chunks into every PEER's recv[0] slot only
     host0, host1 = wins[0].cpu().numpy(), wins[1].cpu().numpy()
     assert not host0[0:g * S].any(), "-2 must not touch the local slot (and a push lands nothing at home)"
     assert host1[0:S].any() and not host1[S:g * S].any()
