@@ -179,6 +179,11 @@ int b200probe_hbm_copy (int cuda_ordinal, const void* src, void* dst, uint64_t b
                         const b200probe_hbm_cfg_t* tuning_or_null, void* stream);
 int b200probe_hbm_read (int cuda_ordinal, const void* src, uint64_t bytes, uint64_t* partials,
                         const b200probe_hbm_cfg_t* tuning_or_null, void* stream);
+/* The probe's verdict pass on any device buffer: checksum (sum64, xor32 of the u32 words) plus a
+ * device-side compare with the closed-form pattern under `seed`: number of words that differ and the
+ * index of the lowest one (~0 when none).  TMA-staged like the read sweep.  Synchronous. */
+int b200probe_hbm_verify(int cuda_ordinal, const void* buf, uint64_t bytes, uint32_t seed,
+                         uint64_t* sum64, uint32_t* xor32, uint64_t* bad_words, uint64_t* first_bad_word);
 /* Host-buffer entry (the data-carrying e2e form): src_host -> H2D -> copy kernel -> checksum of what
  * landed -> D2H into dst_host, pipelined over 8 MiB chunks on three streams so both PCIe directions
  * and the kernel overlap.  Any host memory works; pinned buffers from b200probe_host_alloc reach the

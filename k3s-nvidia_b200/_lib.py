@@ -188,6 +188,7 @@ SIGNATURES = {
     "b200probe_hbm_copy": (C.c_int, [C.c_int, _vp, _vp, C.c_uint64, _P(HbmCfg), _vp]),
     "b200probe_hbm_read": (C.c_int, [C.c_int, _vp, C.c_uint64, _vp, _P(HbmCfg), _vp]),
     "b200probe_hbm_copy_host": (C.c_int, [C.c_int, _vp, _vp, C.c_uint64, _P(C.c_uint64), _P(C.c_uint32)]),
+    "b200probe_hbm_verify": (C.c_int, [C.c_int, _vp, C.c_uint64, C.c_uint32, _P(C.c_uint64), _P(C.c_uint32), _P(C.c_uint64), _P(C.c_uint64)]),
     "b200probe_host_alloc": (C.c_int, [C.c_uint64, _P(_vp)]),
     "b200probe_host_free": (C.c_int, [_vp]),
     "b200probe_nvlink_a2a": (C.c_int, [_P(C.c_int), C.c_int, _P(A2aCfg), _P(C.c_double), _P(A2aResult)]),

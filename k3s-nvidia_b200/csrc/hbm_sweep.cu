@@ -25,6 +25,7 @@ using namespace b200ptx;
 
 constexpr int kMaxWarps = 8;
 constexpr int kMaxStages = 8;
+constexpr int kModeVerify = 8;    // internal: READ + compare with the regenerated pattern (partials[2] bad words, [3] first bad word)
 
 struct RingArgs {
     const uint8_t* src;
@@ -33,7 +34,7 @@ struct RingArgs {
     uint32_t seed;
     uint32_t stage_bytes;      // multiple of 512
     uint32_t stages;           // 2..kMaxStages
-    unsigned long long* partials;   // [0] sum64, [1] xor (read mode)
+    unsigned long long* partials;   // [0] sum64, [1] xor (read mode); verify adds [2] mismatching words, [3] lowest mismatching word
 };
 
 __device__ __forceinline__ void accum16(const uint4& v, unsigned long long& sum, uint32_t& x) {
@@ -60,16 +61,20 @@ __device__ __forceinline__ void tail_words(int mode, const RingArgs& a, uint64_t
     unsigned long long sum = 0;
     uint32_t x = 0;
     for (uint64_t off = bulk_bytes; off < a.bytes; off += 4) {
-        if (mode == B200PROBE_HBM_READ) {
+        if (mode == B200PROBE_HBM_READ || mode == kModeVerify) {
             uint32_t w = *reinterpret_cast<const uint32_t*>(a.src + off);
             sum += w; x ^= w;
+            if (mode == kModeVerify && w != b200_pattern_word(off >> 2, a.seed)) {
+                atomicAdd(a.partials + 2, 1ull);
+                atomicMin(a.partials + 3, (unsigned long long)(off >> 2));
+            }
         } else if (mode == B200PROBE_HBM_WRITE) {
             *reinterpret_cast<uint32_t*>(a.dst + off) = b200_pattern_word(off >> 2, a.seed);
         } else {
             *reinterpret_cast<uint32_t*>(a.dst + off) = *reinterpret_cast<const uint32_t*>(a.src + off);
         }
     }
-    if (mode == B200PROBE_HBM_READ && bulk_bytes < a.bytes) {
+    if ((mode == B200PROBE_HBM_READ || mode == kModeVerify) && bulk_bytes < a.bytes) {
         atomicAdd(a.partials, sum);
         atomicXor(a.partials + 1, (unsigned long long)x);
     }
@@ -134,7 +139,7 @@ __global__ void __launch_bounds__(kMaxWarps * 32) hbm_ring_kernel(RingArgs a) {
             }
             bulk_wait_all();
         }
-    } else if (MODE == B200PROBE_HBM_READ) {
+    } else if (MODE == B200PROBE_HBM_READ || MODE == kModeVerify) {
         unsigned long long sum = 0;
         uint32_t x = 0;
         if (lane == 0) {
@@ -146,11 +151,44 @@ __global__ void __launch_bounds__(kMaxWarps * 32) hbm_ring_kernel(RingArgs a) {
             const uint4* st = reinterpret_cast<const uint4*>(ring_ptr + (size_t)cs * SB);
             const uint32_t nvec = chunk_len(k) >> 4;
             uint32_t i = lane;
-            for (; i + 96 < nvec; i += 128) {
-                uint4 v0 = st[i], v1 = st[i + 32], v2 = st[i + 64], v3 = st[i + 96];
-                accum16(v0, sum, x); accum16(v1, sum, x); accum16(v2, sum, x); accum16(v3, sum, x);
+            if (MODE == kModeVerify) {
+                // word w of the buffer must be (u32)w * K ^ seed ^ (w >> 32); a chunk never straddles a 2^32-word
+                // boundary (chunk offsets are multiples of the stage size), so the high part folds into one constant
+                const uint64_t w0 = chunk_off(k) >> 2;
+                const uint32_t c = a.seed ^ (uint32_t)(w0 >> 32);
+                const uint32_t K = 2654435761u;
+                const uint32_t e0 = (uint32_t)w0 * K;
+                uint32_t diff = 0;
+                auto cmp = [&](const uint4& v, uint32_t vi) {
+                    const uint32_t e = e0 + vi * (4u * K);
+                    diff |= (v.x ^ e ^ c) | (v.y ^ (e + K) ^ c) | (v.z ^ (e + 2u * K) ^ c) | (v.w ^ (e + 3u * K) ^ c);
+                };
+                for (; i + 96 < nvec; i += 128) {
+                    uint4 v0 = st[i], v1 = st[i + 32], v2 = st[i + 64], v3 = st[i + 96];
+                    accum16(v0, sum, x); accum16(v1, sum, x); accum16(v2, sum, x); accum16(v3, sum, x);
+                    cmp(v0, i); cmp(v1, i + 32); cmp(v2, i + 64); cmp(v3, i + 96);
+                }
+                for (; i < nvec; i += 32) { uint4 v = st[i]; accum16(v, sum, x); cmp(v, i); }
+                if (__any_sync(0xffffffffu, diff != 0)) {
+                    // slow path, only for a stage that holds a fault: exact count and lowest index
+                    unsigned long long bad = 0, first = ~0ull;
+                    const uint32_t* wds = reinterpret_cast<const uint32_t*>(st);
+                    for (uint32_t j = lane; j < nvec * 4; j += 32)
+                        if (wds[j] != b200_pattern_word(w0 + j, a.seed)) { ++bad; first = min(first, (unsigned long long)(w0 + j)); }
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) {
+                        bad += __shfl_xor_sync(0xffffffffu, bad, o);
+                        first = min(first, (unsigned long long)__shfl_xor_sync(0xffffffffu, first, o));
+                    }
+                    if (lane == 0 && bad) { atomicAdd(a.partials + 2, bad); atomicMin(a.partials + 3, first); }
+                }
+            } else {
+                for (; i + 96 < nvec; i += 128) {
+                    uint4 v0 = st[i], v1 = st[i + 32], v2 = st[i + 64], v3 = st[i + 96];
+                    accum16(v0, sum, x); accum16(v1, sum, x); accum16(v2, sum, x); accum16(v3, sum, x);
+                }
+                for (; i < nvec; i += 32) accum16(st[i], sum, x);
             }
-            for (; i < nvec; i += 32) accum16(st[i], sum, x);
             __syncwarp();
             // lane 0 is the only producer: its `issued` counts k+S loads here, stage ps == cs
             if (lane == 0 && k + S < n_my) load_next();
@@ -303,7 +341,7 @@ struct Tuning {
 Tuning resolve_tuning(const b200probe_hbm_cfg_t* c, int mode) {
     Tuning t;
     t.variant = c ? c->variant : B200PROBE_VARIANT_TMA;
-    const int d_stages = mode == B200PROBE_HBM_COPY ? 4 : mode == B200PROBE_HBM_READ ? 3 : 6;
+    const int d_stages = mode == B200PROBE_HBM_COPY ? 4 : (mode == B200PROBE_HBM_READ || mode == kModeVerify) ? 3 : 6;
     const int d_warps = mode == B200PROBE_HBM_COPY ? 2 : 4;
     t.stage_bytes = (c && c->stage_bytes) ? c->stage_bytes : 8192;
     t.stages = (c && c->stages) ? c->stages : d_stages;
@@ -424,14 +462,28 @@ int arena_reserve(Arena& a, uint64_t bytes, uint64_t flush_bytes) {
     return 0;
 }
 
+// Verification launch: the TMA-ring read kernel with the pattern compare folded in (same staging and
+// tuning as the read sweep, so the verdict pass runs at read bandwidth); B200PROBE_VERIFY_DIRECT=1 selects
+// the LDG grid-stride kernel instead (A/B checks).
+int launch_verify(int ordinal, const uint8_t* buf, uint64_t bytes, uint32_t seed, unsigned long long* partials, cudaStream_t stream, int sms) {
+    static const bool direct = [] { const char* e = getenv("B200PROBE_VERIFY_DIRECT"); return e && *e == '1'; }();
+    if (direct || (((uintptr_t)buf) & 15)) {
+        hbm_verify_kernel<<<sms * 4, 512, 0, stream>>>(buf, bytes, seed, partials);
+        B200_CUDA_TRY(cudaGetLastError());
+        return 0;
+    }
+    RingArgs a{buf, nullptr, bytes, seed, 0, 0, partials};
+    return launch_mode<kModeVerify>(ordinal, a, nullptr, stream);
+}
+
 struct VerifyOut { uint64_t sum; uint32_t x; uint64_t bad, first; };
 
 int verify_pass(int ordinal, const uint8_t* buf, uint64_t bytes, uint32_t seed, Arena& a, int sms, VerifyOut* v) {
     static const unsigned long long init[4] = {0, 0, 0, ~0ull};
     B200_CUDA_TRY(cudaMemcpyAsync(a.partials, init, 32, cudaMemcpyHostToDevice, a.stream));
     if (bytes) {
-        hbm_verify_kernel<<<sms * 4, 512, 0, a.stream>>>(buf, bytes, seed, a.partials);
-        B200_CUDA_TRY(cudaGetLastError());
+        int rc = launch_verify(ordinal, buf, bytes, seed, a.partials, a.stream, sms);
+        if (rc) return rc;
     }
     unsigned long long h[4];
     B200_CUDA_TRY(cudaMemcpyAsync(h, a.partials, 32, cudaMemcpyDeviceToHost, a.stream));
@@ -453,8 +505,8 @@ int verify_pattern(int ordinal, const void* buf, uint64_t bytes, uint32_t seed, 
     B200_CUDA_TRY(cudaSetDevice(ordinal));
     B200_CUDA_TRY(cudaMemcpyAsync(d_partials, init, 32, cudaMemcpyHostToDevice, st));
     if (bytes) {
-        hbm_verify_kernel<<<props.sms * 4, 512, 0, st>>>((const uint8_t*)buf, bytes, seed, d_partials);
-        B200_CUDA_TRY(cudaGetLastError());
+        rc = launch_verify(ordinal, (const uint8_t*)buf, bytes, seed, d_partials, st, props.sms);
+        if (rc) return rc;
     }
     unsigned long long h[4];
     B200_CUDA_TRY(cudaMemcpyAsync(h, d_partials, 32, cudaMemcpyDeviceToHost, st));
@@ -486,6 +538,28 @@ int b200probe_hbm_read(int ordinal, const void* src, uint64_t bytes, uint64_t* p
     if (!partials) return B200PROBE_EINVAL;
     RingArgs a{(const uint8_t*)src, nullptr, bytes, 0, 0, 0, (unsigned long long*)partials};
     return launch_mode<B200PROBE_HBM_READ>(ordinal, a, cfg, (cudaStream_t)stream);
+}
+
+int b200probe_hbm_verify(int ordinal, const void* buf, uint64_t bytes, uint32_t seed, uint64_t* sum64, uint32_t* xor32,
+                         uint64_t* bad_words, uint64_t* first_bad_word) {
+    int rc = check_args(buf, nullptr, bytes);
+    if (rc) return rc;
+    b200::DevProps props;
+    rc = b200::device_props(ordinal, &props);
+    if (rc) return rc;
+    B200_CUDA_TRY(cudaSetDevice(ordinal));
+    Arena& a = g_arena[ordinal];
+    ArenaLock lock(a);
+    rc = arena_reserve(a, 0, 0);
+    if (rc) return rc;
+    VerifyOut v;
+    rc = verify_pass(ordinal, (const uint8_t*)buf, bytes, seed, a, props.sms, &v);
+    if (rc) return rc;
+    if (sum64) *sum64 = v.sum;
+    if (xor32) *xor32 = v.x;
+    if (bad_words) *bad_words = v.bad;
+    if (first_bad_word) *first_bad_word = v.first;
+    return 0;
 }
 
 int b200probe_host_alloc(uint64_t bytes, void** ptr) {

@@ -215,6 +215,13 @@ class Probe:
                     "hbm_copy_host")
         return s64.value, x32.value
 
+    def hbm_verify(self, ordinal: int, ptr: int, nbytes: int, seed: int):
+        """Verdict pass on a device buffer -> (sum64, xor32, bad_words, first_bad_word)."""
+        s64, x32, bad, first = C.c_uint64(), C.c_uint32(), C.c_uint64(), C.c_uint64()
+        self._check(self.lib.b200probe_hbm_verify(ordinal, ptr, nbytes, seed, C.byref(s64), C.byref(x32), C.byref(bad), C.byref(first)),
+                    "hbm_verify")
+        return s64.value, x32.value, bad.value, first.value
+
     def host_alloc(self, nbytes: int):
         """Pinned host buffer as a numpy uint8 array (free with host_free(arr))."""
         import numpy as np

@@ -51,6 +51,15 @@ void oracle_pattern_checksum(uint64_t words, uint32_t seed, uint64_t* sum64, uin
     *xor32 = x;
 }
 
+/* The probe's verdict pass restated: words of buf that differ from the pattern, and the lowest such index
+ * (UINT64_MAX when none).  buf holds words [first_word, first_word + words). */
+void oracle_verify(const uint32_t* buf, uint64_t first_word, uint64_t words, uint32_t seed, uint64_t* bad, uint64_t* first_bad) {
+    uint64_t n = 0, f = UINT64_MAX;
+    for (uint64_t i = 0; i < words; ++i)
+        if (buf[i] != pat(first_word + i, seed)) { if (!n) f = first_word + i; ++n; }
+    *bad = n; *first_bad = f;
+}
+
 void oracle_copy(void* dst, const void* src, uint64_t bytes) { memmove(dst, src, bytes); }
 
 /* ---- multi-threaded host sweep: the "port" CPU baseline --------------------------------------

@@ -20,6 +20,7 @@ def load():
     o.oracle_checksum.argtypes = [C.c_void_p, C.c_uint64, u64p, u32p]
     o.oracle_pattern_checksum.argtypes = [C.c_uint64, C.c_uint32, u64p, u32p]
     o.oracle_copy.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64]
+    o.oracle_verify.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint32, u64p, u64p]
     o.oracle_host_sweep.restype = C.c_double
     o.oracle_host_sweep.argtypes = [C.c_uint64, C.c_int, C.c_int, C.c_int, C.c_uint32, u64p, u32p]
     o.oracle_a2a_chunk_seed.restype = C.c_uint32
@@ -53,6 +54,13 @@ def checksum(o, arr):
     s, x = C.c_uint64(), C.c_uint32()
     o.oracle_checksum(arr.ctypes.data, arr.nbytes // 4, C.byref(s), C.byref(x))
     return s.value, x.value
+
+
+def verify(o, arr, seed, first_word=0):
+    """(bad_words, first_bad_word) of a C-contiguous numpy buffer against the pattern; first = 2**64-1 when clean."""
+    bad, first = C.c_uint64(), C.c_uint64()
+    o.oracle_verify(arr.ctypes.data, first_word, arr.nbytes // 4, seed, C.byref(bad), C.byref(first))
+    return bad.value, first.value
 
 
 def pattern(o, first_word, words, seed):

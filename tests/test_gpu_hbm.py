@@ -64,6 +64,72 @@ def test_read_checksum_of_arbitrary_data(env):
         assert _dev_checksum(torch, p, dev, host.numel(), **tuning) == _oracle.checksum(o, host.numpy())
 
 
+@pytest.mark.parametrize("direct", [False, True], ids=["tma-ring", "ldg"])
+def test_verdict_pass_finds_injected_faults(env, direct, monkeypatch):
+    """The probe's own verdict: flipped bits anywhere in the swept range are counted and located exactly
+    as the oracle does (single bit, bursts, first/last word, ragged tail, fault in the non-16-byte tail)."""
+    import subprocess, sys, json, os
+
+    torch, p, o = env
+    if direct:
+        # the kernel choice is latched per process: run the same cases in a child with the LDG kernel selected
+        code = ("import sys, json; sys.path.insert(0, %r); sys.path.insert(0, %r); import test_gpu_hbm as t; print(json.dumps(t._fault_cases()))"
+                % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), os.path.dirname(os.path.abspath(__file__))))
+        out = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, B200PROBE_VERIFY_DIRECT="1"), capture_output=True, text=True, timeout=300)
+        assert out.returncode == 0, out.stderr[-2000:]
+        assert json.loads(out.stdout.strip().splitlines()[-1]) == "ok"
+    else:
+        assert _fault_cases() == "ok"
+
+
+def _fault_cases():
+    import torch
+
+    from k3s_nvidia_b200.probe import Probe
+
+    p, o = Probe(), _oracle.load()
+    st = torch.cuda.current_stream().cuda_stream
+    for nbytes in ((8 << 20), (5 << 20) + 8192 + 12, 52, 16):
+        words = nbytes // 4
+        buf = torch.empty(nbytes, dtype=torch.uint8, device="cuda:0")
+        p.hbm_fill(0, buf.data_ptr(), nbytes, SEED, st)
+        torch.cuda.synchronize()
+        clean = _oracle.pattern_checksum(o, words, SEED)
+        assert p.hbm_verify(0, buf.data_ptr(), nbytes, SEED) == (clean[0], clean[1], 0, 2**64 - 1)
+        assert p.hbm_verify(0, buf.data_ptr(), nbytes, SEED ^ 1)[2] == words          # wrong seed: every word differs
+        w32 = buf.view(torch.int32)
+        rng = np.random.default_rng(nbytes)
+        cases = [[0], [words - 1], sorted(rng.choice(words, size=min(words, 7), replace=False).tolist()),
+                 list(range(max(0, words // 2 - 3), min(words, words // 2 + 40)))]
+        for idxs in cases:
+            keep = w32[idxs].clone()
+            w32[idxs] = w32[idxs] ^ torch.tensor([1 << (i % 31) for i in idxs], dtype=torch.int32, device="cuda:0")
+            host = buf.cpu().numpy()
+            want_bad, want_first = _oracle.verify(o, host.view(np.uint32), SEED)
+            s, x, bad, first = p.hbm_verify(0, buf.data_ptr(), nbytes, SEED)
+            assert (bad, first) == (want_bad, want_first) == (len(idxs), idxs[0]), (nbytes, idxs[:4], bad, first)
+            assert (s, x) == _oracle.checksum(o, host.view(np.uint32))
+            w32[idxs] = keep
+        assert p.hbm_verify(0, buf.data_ptr(), nbytes, SEED)[2] == 0
+    return "ok"
+
+
+def test_verdict_pass_on_a_blank_buffer_and_bad_arguments(env):
+    """A buffer that never received the pattern: every word that the pattern says is non-zero counts."""
+    torch, p, o = env
+    from k3s_nvidia_b200.probe import ProbeError
+
+    nbytes = 1 << 20
+    buf = torch.zeros(nbytes, dtype=torch.uint8, device="cuda:0")
+    want = _oracle.pattern(o, 0, nbytes // 4, SEED)
+    s, x, bad, first = p.hbm_verify(0, buf.data_ptr(), nbytes, SEED)
+    assert (s, x) == (0, 0) and bad == int(np.count_nonzero(want)) and first == int(np.flatnonzero(want)[0])
+    with pytest.raises(ProbeError):
+        p.hbm_verify(0, buf.data_ptr() + 4, 1 << 10, SEED)          # misaligned pointer
+    with pytest.raises(ProbeError):
+        p.hbm_verify(0, buf.data_ptr(), 1022, SEED)                 # not a multiple of 4
+
+
 def test_copy_host_roundtrip(env):
     torch, p, o = env
     rng = np.random.default_rng(3)

@@ -77,3 +77,20 @@ def test_host_sweep_port_results(o):
         dt = o.oracle_host_sweep(1 << 22, 3, mode, 2, 0xB200, C.byref(s), C.byref(x))
         assert dt > 0
         assert (s.value, x.value) == _oracle.pattern_checksum(o, (1 << 22) // 4, 0xB200)
+
+
+def test_verify_counts_and_locates_faults(o):
+    """oracle_verify (the checker of the device verdict pass) against a pure-Python restatement of
+    the pattern rule taken from the golden generator, across the 2^32-word boundary."""
+    K = 2654435761
+    def pat(i, seed):
+        return ((i & 0xFFFFFFFF) * K & 0xFFFFFFFF) ^ seed ^ (i >> 32)
+    for first_word in (0, 2**32 - 5):
+        a = _oracle.pattern(o, first_word, 64, 0xB200)
+        assert [int(v) for v in a] == [pat(first_word + j, 0xB200) for j in range(64)]
+        assert _oracle.verify(o, a, 0xB200, first_word) == (0, 2**64 - 1)
+        b = a.copy()
+        for j in (3, 9, 63):
+            b[j] ^= np.uint32(1 << (j % 32))
+        assert _oracle.verify(o, b, 0xB200, first_word) == (3, first_word + 3)
+        assert _oracle.verify(o, a, 0xB201, first_word) == (64, first_word)
