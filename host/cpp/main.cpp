@@ -1,0 +1,138 @@
+// b200-device-plugin — the container entry point that stands where the upstream plugin binary stands inside
+// the nvdp DaemonSet (/root/reference/README.md:116): reads the plugin config document the chart mounts
+// (/root/reference/values.yaml:8-18), serves the kubelet device-plugin API v1beta1 on a unix socket,
+// registers with kubelet, follows the passive XID/ECC health events, and (unless --no-active-probe) runs the
+// B200 active probes at an interval and publishes their verdicts as NFD labels.
+//
+//   b200-device-plugin --config-file /config/config.yaml
+//   b200-device-plugin --check-config FILE          print the parsed configuration as JSON (parity tests)
+//   b200-device-plugin --probe-once                 one active-probe round, labels on stdout
+#include <signal.h>
+
+#include <fstream>
+#include <iostream>
+#include <sstream>
+
+#include "labels.hpp"
+#include "plugin.hpp"
+
+static std::atomic<bool> g_stop{false};
+static void on_signal(int) { g_stop = true; }
+
+static std::string json_str(const std::string& s) {
+    std::string o = "\"";
+    for (unsigned char c : s) {
+        if (c == '"' || c == '\\') { o += '\\'; o += (char)c; }
+        else if (c < 0x20 || c >= 0x7f) { char b[8]; snprintf(b, sizeof(b), "\\u%04x", c); o += b; }
+        else o += (char)c;
+    }
+    return o + "\"";
+}
+
+// stdin: one hex-encoded header block per line, decoded by ONE decoder in order (dynamic-table continuity);
+// stdout: one JSON array of [name, value] pairs per block, or {"error": ...}.  Transport self-check used by the tests.
+static int hpack_decode_stdin() {
+    hpack::Decoder dec;
+    std::string line;
+    while (std::getline(std::cin, line)) {
+        std::string bytes;
+        for (size_t i = 0; i + 1 < line.size(); i += 2) bytes.push_back((char)strtol(line.substr(i, 2).c_str(), nullptr, 16));
+        std::vector<hpack::Header> hs;
+        if (!dec.decode((const uint8_t*)bytes.data(), bytes.size(), &hs)) { printf("{\"error\":\"decode failed\"}\n"); continue; }
+        std::string o = "[";
+        for (size_t i = 0; i < hs.size(); ++i) o += std::string(i ? "," : "") + "[" + json_str(hs[i].first) + "," + json_str(hs[i].second) + "]";
+        printf("%s]\n", o.c_str());
+    }
+    return 0;
+}
+
+static int check_config(const std::string& path) {
+    std::ifstream f(path);
+    std::stringstream ss;
+    ss << f.rdbuf();
+    try {
+        const config::PluginConfig c = config::parse_plugin_config(ss.str());
+        std::string res = "[";
+        for (size_t i = 0; i < c.time_slicing.resources.size(); ++i) {
+            const auto& r = c.time_slicing.resources[i];
+            res += std::string(i ? "," : "") + "{\"name\":" + json_str(r.name) + ",\"replicas\":" + std::to_string(r.replicas) +
+                   ",\"rename\":" + (r.rename.empty() ? "null" : json_str(r.rename)) + "}";
+        }
+        res += "]";
+        printf("{\"ok\":true,\"version\":%s,\"mig_strategy\":%s,\"device_list_strategy\":%s,\"device_id_strategy\":%s,\"pass_device_specs\":%s,"
+               "\"rename_by_default\":%s,\"fail_requests_greater_than_one\":%s,\"resources\":%s,\"resource_name\":%s,\"replicas\":%lld,\"is_shared\":%s}\n",
+               json_str(c.version).c_str(), json_str(c.mig_strategy).c_str(), json_str(c.device_list_strategy).c_str(), json_str(c.device_id_strategy).c_str(),
+               c.pass_device_specs ? "true" : "false", c.time_slicing.rename_by_default ? "true" : "false",
+               c.time_slicing.fail_requests_greater_than_one ? "true" : "false", res.c_str(), json_str(c.resource_name()).c_str(), (long long)c.replicas(),
+               c.is_shared() ? "true" : "false");
+        return 0;
+    } catch (const config::Error& e) {
+        printf("{\"ok\":false,\"error\":%s}\n", json_str(e.what()).c_str());
+        return 0;
+    }
+}
+
+int main(int argc, char** argv) {
+    std::string config_file = getenv("CONFIG_FILE") ? getenv("CONFIG_FILE") : "/config/config.yaml";
+    std::string socket_dir = v1beta1::kDevicePluginPath, kubelet_socket, nvml_path;
+    std::string features_dir = "/etc/kubernetes/node-feature-discovery/features.d";
+    double probe_interval = getenv("B200PROBE_INTERVAL_S") ? atof(getenv("B200PROBE_INTERVAL_S")) : 600.0, watch_period = 1.0;
+    bool active = true, probe_once = false, health = true;
+    int health_timeout_ms = 5000;
+    for (int i = 1; i < argc; ++i) {
+        const std::string a = argv[i];
+        auto val = [&](std::string* out) { if (i + 1 >= argc) { fprintf(stderr, "%s needs a value\n", a.c_str()); exit(2); } *out = argv[++i]; };
+        std::string v;
+        if (a == "--check-config") { val(&v); return check_config(v); }
+        else if (a == "--hpack-decode") return hpack_decode_stdin();
+        else if (a == "--config-file") val(&config_file);
+        else if (a == "--socket-dir") val(&socket_dir);
+        else if (a == "--kubelet-socket") val(&kubelet_socket);
+        else if (a == "--features-dir") val(&features_dir);
+        else if (a == "--nvml-path") val(&nvml_path);
+        else if (a == "--probe-interval") { val(&v); probe_interval = atof(v.c_str()); }
+        else if (a == "--watch-period") { val(&v); watch_period = atof(v.c_str()); }
+        else if (a == "--health-timeout-ms") { val(&v); health_timeout_ms = atoi(v.c_str()); }
+        else if (a == "--no-active-probe") active = false;
+        else if (a == "--no-health") health = false;
+        else if (a == "--probe-once") probe_once = true;
+        else if (a == "--version") { printf("b200-device-plugin abi %d\n", b200probe_abi_version()); return 0; }
+        else { fprintf(stderr, "unknown argument %s\n", a.c_str()); return 2; }
+    }
+    int rc = b200probe_init(nvml_path.empty() ? nullptr : nvml_path.c_str());
+    if (rc) { plugin::logf("b200probe_init failed: %s", b200probe_strerror(rc)); return 1; }
+    if (probe_once) {
+        try {
+            labels::ActiveProbeRunner runner(features_dir, 0);
+            fputs(labels::render(runner.run_once()).c_str(), stdout);
+            return 0;
+        } catch (const std::exception& e) { plugin::logf("probe round failed: %s", e.what()); return 1; }
+    }
+    config::PluginConfig cfg;
+    try {
+        std::ifstream f(config_file);
+        if (!f) throw config::Error("cannot open " + config_file);
+        std::stringstream ss;
+        ss << f.rdbuf();
+        cfg = config::parse_plugin_config(ss.str());
+    } catch (const std::exception& e) { plugin::logf("config: %s", e.what()); return 1; }
+
+    struct sigaction sa;
+    memset(&sa, 0, sizeof(sa));
+    sa.sa_handler = on_signal;
+    sigaction(SIGTERM, &sa, nullptr);
+    sigaction(SIGINT, &sa, nullptr);
+    signal(SIGPIPE, SIG_IGN);
+    try {
+        plugin::DevicePlugin dp(cfg, socket_dir, kubelet_socket, health_timeout_ms);
+        dp.start(watch_period, health);
+        std::unique_ptr<labels::ActiveProbeRunner> runner;
+        if (active) { runner.reset(new labels::ActiveProbeRunner(features_dir, probe_interval)); runner->start(); }
+        plugin::logf("serving '%s' on %s (%zu devices)", dp.resource().c_str(), dp.socket_path().c_str(), dp.devices().size());
+        while (!g_stop) usleep(100000);
+        if (runner) runner->stop();
+        dp.stop();
+    } catch (const std::exception& e) { plugin::logf("fatal: %s", e.what()); b200probe_shutdown(); return 1; }
+    b200probe_shutdown();
+    return 0;
+}

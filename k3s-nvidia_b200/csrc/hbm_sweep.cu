@@ -294,9 +294,10 @@ __global__ void __launch_bounds__(512) hbm_verify_kernel(const uint8_t* __restri
         const uint32_t d = (v.x ^ b200_pattern_word(w, seed)) | (v.y ^ b200_pattern_word(w + 1, seed)) |
                            (v.z ^ b200_pattern_word(w + 2, seed)) | (v.w ^ b200_pattern_word(w + 3, seed));
         if (d) {
-            bad += (v.x != b200_pattern_word(w, seed)) + (v.y != b200_pattern_word(w + 1, seed)) + (v.z != b200_pattern_word(w + 2, seed)) +
-                   (v.w != b200_pattern_word(w + 3, seed));
-            first = min(first, (unsigned long long)w);
+            const bool bx = v.x != b200_pattern_word(w, seed), by = v.y != b200_pattern_word(w + 1, seed), bz = v.z != b200_pattern_word(w + 2, seed),
+                       bw = v.w != b200_pattern_word(w + 3, seed);
+            bad += bx + by + bz + bw;
+            first = min(first, (unsigned long long)(w + (bx ? 0 : by ? 1 : bz ? 2 : 3)));     // exact word, not the vector it sits in
         }
     };
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;

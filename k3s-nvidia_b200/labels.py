@@ -35,7 +35,8 @@ HBM_NOMINAL_GBS = 8000.0         # north_star's denominator
 HBM_MEASURED_GBS = 6565.8        # MEASURED_PEAKS.json hbm_gbs (torch copy_, read+write bytes)
 NVLINK_NOMINAL_GBS = 900.0       # per direction per GPU
 NVLINK_MEASURED_GBS = 770.0      # /opt/skills/guides/B200_PROFILING.md: peer copy per direction
-NVLINK_HEALTHY_GBS = 692.0       # this repo's push kernel with all 18 links up (profiles/a2a_tune_r01_2gpu.txt, +-0.3%)
+NVLINK_HEALTHY_GBS = 692.0       # this repo's push kernel with all 18 links up, G = 2 (profiles/a2a_tune_r01_2gpu.txt, +-0.3%)
+NVLINK_HEALTHY_GBS_BOX = 673.0   # G > 2: one peer per step with the step barrier (profiles/a2a_sync_r01_g8.txt; 680 across processes)
 GEMM_NOMINAL_TFLOPS = 2250.0
 GEMM_MEASURED_TFLOPS = 1670.2
 
@@ -53,8 +54,9 @@ def _env_float(name: str, default: float) -> float:
 @dataclass
 class Thresholds:
     hbm_min_gbs: float = field(default_factory=lambda: _env_float("B200PROBE_HBM_MIN_GBS", 0.90 * HBM_MEASURED_GBS))
-    # one dead link of 18 costs 5.6% (692 -> ~654 GB/s): the gate sits 3% under the healthy figure
-    nvlink_min_gbs: float = field(default_factory=lambda: _env_float("B200PROBE_NVLINK_MIN_GBS", 0.97 * NVLINK_HEALTHY_GBS))
+    # one dead link of 18 costs 5.6% (692 -> ~654 GB/s): the gate sits 3% under the healthy figure for the
+    # number of GPUs exchanged (0 = derive from G when the labels are made; B200PROBE_NVLINK_MIN_GBS pins it)
+    nvlink_min_gbs: float = field(default_factory=lambda: _env_float("B200PROBE_NVLINK_MIN_GBS", 0.0))
     gemm_min_tflops: float = field(default_factory=lambda: _env_float("B200PROBE_GEMM_MIN_TFLOPS", 0.70 * GEMM_MEASURED_TFLOPS))
     verdict_min_bytes: int = 256 << 20        # sizes below L2 are cache-resident: never used for the verdict
 
@@ -108,10 +110,11 @@ def nvlink_labels(rep, th: Thresholds) -> Dict[str, str]:
     published per GPU as egress/ingress GB/s plus the cold-spot of the pair matrix."""
     out: Dict[str, str] = {}
     ok = rep.verified != 0
+    min_gbs = th.nvlink_min_gbs or 0.97 * (NVLINK_HEALTHY_GBS if rep.g <= 2 else NVLINK_HEALTHY_GBS_BOX)
     for g in range(rep.g):
         out[f"{PREFIX}gpu{g}.nvlink-egress-gbs"] = str(int(round(rep.egress_gbs[g])))
         out[f"{PREFIX}gpu{g}.nvlink-ingress-gbs"] = str(int(round(rep.ingress_gbs[g])))
-        good = rep.egress_gbs[g] >= th.nvlink_min_gbs
+        good = rep.egress_gbs[g] >= min_gbs
         out[f"{PREFIX}gpu{g}.nvlink-healthy"] = _b(good and rep.verified != 0)
         ok = ok and good
         for p in range(rep.g):

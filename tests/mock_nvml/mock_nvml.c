@@ -11,6 +11,9 @@
  *   MOCK_NVML_EVENTS_QUERY_FAIL=i  nvmlDeviceGetSupportedEventTypes -> UNKNOWN for these
  *   MOCK_NVML_UUID_FAIL=i          nvmlDeviceGetUUID fails for these (enumeration error path)
  *   MOCK_NVML_LINKS_DOWN=d:l,d:l   link l of device d reports NVML_FEATURE_DISABLED
+ *   MOCK_NVML_EVENT_FILE=path      events for a mock living in ANOTHER process (the native daemon): every
+ *                                  wait first queues the lines "kind dev data" appended to the file since
+ *                                  the last wait
  * Events are queued with mock_nvml_push(kind, device, data) and popped one per EventSetWait:
  *   kind 0 = XID critical (data = xid), 1 = double-bit ECC, 2 = single-bit ECC,
  *   kind 3 = wait returns error `data` (nvmlReturn_t), kind 4 = XID on a device whose UUID cannot
@@ -134,10 +137,29 @@ nvmlReturn_t nvmlDeviceRegisterEvents(nvmlDevice_t d, unsigned long long types, 
     if (i < MAXD) g_registered[i] |= types;
     return NVML_SUCCESS;
 }
+static long g_event_file_pos = 0;
+static void drain_event_file(void) {             /* caller holds g_mu */
+    const char* path = getenv("MOCK_NVML_EVENT_FILE");
+    if (!path) return;
+    FILE* f = fopen(path, "r");
+    if (!f) return;
+    if (fseek(f, g_event_file_pos, SEEK_SET) == 0) {
+        char line[128];
+        while (fgets(line, sizeof(line), f)) {
+            if (!strchr(line, '\n')) break;       /* a line still being written: pick it up next time */
+            int kind, dev;
+            unsigned long long data;
+            if (sscanf(line, "%d %d %llu", &kind, &dev, &data) == 3) { g_q[g_qt % 256] = (mev_t){kind, dev, data}; g_qt++; }
+            g_event_file_pos = ftell(f);
+        }
+    }
+    fclose(f);
+}
 nvmlReturn_t nvmlEventSetWait_v2(nvmlEventSet_t s, nvmlEventData_t* data, unsigned int timeoutms) {
     (void)s;
     pthread_mutex_lock(&g_mu);
     g_waits++;
+    drain_event_file();
     if (g_qh == g_qt) {
         pthread_mutex_unlock(&g_mu);
         if (timeoutms) { struct timespec ts = {0, (long)(timeoutms > 2 ? 2 : timeoutms) * 1000000L}; nanosleep(&ts, NULL); }

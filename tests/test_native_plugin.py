@@ -1,0 +1,372 @@
+"""The NATIVE device-plugin host (host/cpp/b200-device-plugin: hand-written HTTP/2 + HPACK + gRPC framing +
+protobuf wire format above the C ABI) against a fake kubelet over real unix-domain gRPC.  Same cases as
+tests/test_plugin.py runs against the Python host: the two hosts must be indistinguishable to kubelet.
+The peer here is grpcio (gRPC C-core), which Huffman-codes and indexes its headers and is strict about
+HTTP/2 framing, so these tests also cover the transport."""
+import json
+import os
+import signal
+import subprocess
+import time
+
+import grpc
+import pytest
+
+import _oracle
+from k3s_nvidia_b200 import api
+from k3s_nvidia_b200 import config as cfgmod
+from test_plugin import FakeKubelet, U0, U1
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+BIN = os.path.join(ROOT, "host", "cpp", "build", "b200-device-plugin")
+G = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "golden.json")))
+VALUES = cfgmod.parse_helm_values(G["reference_inputs"]["values.yaml"]["text"])
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _binary():
+    if not os.path.exists(BIN):
+        subprocess.run(["make", "-C", os.path.join(ROOT, "host", "cpp")], check=True, capture_output=True)
+
+
+class Daemon:
+    def __init__(self, d, config_text, extra_env=None, args=()):
+        self.dir = d
+        self.events = os.path.join(d, "events.txt")
+        open(self.events, "w").close()
+        cfg = os.path.join(d, "config.yaml")
+        with open(cfg, "w") as f:
+            f.write(config_text)
+        env = dict(os.environ, MOCK_NVML_DEVICES="2", MOCK_NVML_EVENT_FILE=self.events)
+        env.update(extra_env or {})
+        self.log = open(os.path.join(d, "daemon.log"), "w")
+        self.proc = subprocess.Popen([BIN, "--config-file", cfg, "--socket-dir", d, "--nvml-path", _oracle.MOCK_NVML, "--no-active-probe",
+                                      "--watch-period", "0.05", "--health-timeout-ms", "5", *args], env=env, stderr=self.log)
+
+    def wait_serving(self, timeout=10.0):
+        """Registered AND past start(): the fake kubelet's handler sets its event before the response is on the
+        wire, so a test that stops the kubelet right away would cut the daemon's initial Register short."""
+        t_end = time.time() + timeout
+        while time.time() < t_end:
+            if " serving '" in self.logtext():
+                return True
+            if self.proc.poll() is not None:
+                return False
+            time.sleep(0.02)
+        return False
+
+    def push(self, kind, dev, data):
+        with open(self.events, "a") as f:
+            f.write(f"{kind} {dev} {data}\n")
+
+    def stop(self):
+        if self.proc.poll() is None:
+            self.proc.send_signal(signal.SIGTERM)
+            try:
+                self.proc.wait(10)
+            except subprocess.TimeoutExpired:
+                self.proc.kill()
+        self.log.close()
+
+    def logtext(self):
+        return open(os.path.join(self.dir, "daemon.log")).read()
+
+
+@pytest.fixture
+def stack(tmp_path):
+    d = str(tmp_path)
+    kubelet = FakeKubelet(d)
+    kubelet.start()
+    daemon = Daemon(d, VALUES.raw_configs["default"])          # the config document exactly as the chart mounts it
+    try:
+        assert kubelet.event.wait(10) and daemon.wait_serving(), "native plugin did not register: " + daemon.logtext()
+        yield kubelet, daemon
+    finally:
+        daemon.stop()
+        kubelet.stop()
+
+
+def test_register_request(stack):
+    kubelet, daemon = stack
+    r = kubelet.requests[0]
+    assert (r.version, r.resource_name, r.endpoint) == ("v1beta1", "nvidia.com/gpu", "nvidia-gpu.sock")
+    assert r.options.get_preferred_allocation_available is True and r.options.pre_start_required is False
+
+
+def test_options_and_list(stack):
+    kubelet, daemon = stack
+    with kubelet.plugin_channel() as ch:
+        stub = api.DevicePluginStub(ch)
+        opts = stub.GetDevicePluginOptions(api.Empty())
+        assert opts.get_preferred_allocation_available and not opts.pre_start_required
+        stream = stub.ListAndWatch(api.Empty())
+        first = next(stream)
+        assert [d.ID for d in first.devices] == [f"{U0}::{r}" for r in range(4)] + [f"{U1}::{r}" for r in range(4)]
+        assert {d.health for d in first.devices} == {"Healthy"}
+        stream.cancel()
+
+
+def test_native_list_is_byte_identical_to_the_python_host(stack, monkeypatch):
+    """Same NVML state, same config -> the serialized ListAndWatchResponse of both hosts is the same bytes."""
+    from k3s_nvidia_b200.plugin import DevicePlugin
+    from k3s_nvidia_b200.probe import Probe
+
+    kubelet, daemon = stack
+    with kubelet.plugin_channel() as ch:
+        raw = ch.unary_stream("/v1beta1.DevicePlugin/ListAndWatch", request_serializer=lambda m: m.SerializeToString(), response_deserializer=lambda b: b)
+        stream = raw(api.Empty())
+        native = next(stream)
+        stream.cancel()
+    monkeypatch.setenv("MOCK_NVML_DEVICES", "2")
+    probe = Probe(_oracle.MOCK_NVML)
+    try:
+        py = DevicePlugin(probe, VALUES.default, socket_dir=str(daemon.dir) + "/py")
+        want = api.ListAndWatchResponse(devices=py.api_devices()).SerializeToString()
+    finally:
+        probe.close()
+    assert native == want
+
+
+def test_xid_turns_every_replica_of_that_gpu_unhealthy_and_resends_full_list(stack):
+    kubelet, daemon = stack
+    with kubelet.plugin_channel() as ch:
+        stream = api.DevicePluginStub(ch).ListAndWatch(api.Empty())
+        next(stream)
+        daemon.push(0, 1, 79)                    # critical XID on GPU 1
+        upd = next(stream)
+        assert len(upd.devices) == 8             # the COMPLETE list, not a delta
+        health = {d.ID: d.health for d in upd.devices}
+        assert all(health[f"{U1}::{r}"] == "Unhealthy" for r in range(4))
+        assert all(health[f"{U0}::{r}"] == "Healthy" for r in range(4))
+        daemon.push(0, 0, 13)                    # application XID: skipped, no update
+        daemon.push(0, 0, 48)                    # then a critical one on GPU 0
+        upd = next(stream)
+        assert {d.health for d in upd.devices} == {"Unhealthy"}
+        stream.cancel()
+
+
+def test_allocate_strips_replicas_and_dedupes(stack):
+    kubelet, daemon = stack
+    with kubelet.plugin_channel() as ch:
+        stub = api.DevicePluginStub(ch)
+        resp = stub.Allocate(api.AllocateRequest(container_requests=[api.ContainerAllocateRequest(devices_ids=[f"{U0}::2"])]))
+        assert dict(resp.container_responses[0].envs) == {"NVIDIA_VISIBLE_DEVICES": U0}
+        resp = stub.Allocate(api.AllocateRequest(container_requests=[
+            api.ContainerAllocateRequest(devices_ids=[f"{U0}::0", f"{U0}::3"]),
+            api.ContainerAllocateRequest(devices_ids=[f"{U1}::1", f"{U0}::1"])]))
+        assert dict(resp.container_responses[0].envs) == {"NVIDIA_VISIBLE_DEVICES": U0}
+        assert dict(resp.container_responses[1].envs) == {"NVIDIA_VISIBLE_DEVICES": f"{U1},{U0}"}
+        assert len(resp.container_responses[0].mounts) == 0 and len(resp.container_responses[0].devices) == 0
+        with pytest.raises(grpc.RpcError) as e:
+            stub.Allocate(api.AllocateRequest(container_requests=[api.ContainerAllocateRequest(devices_ids=["GPU-nope::0"])]))
+        assert e.value.code() == grpc.StatusCode.UNKNOWN
+        assert e.value.details() == "invalid allocation request for 'nvidia.com/gpu': unknown device: GPU-nope::0"
+        assert stub.PreStartContainer(api.PreStartContainerRequest(devices_ids=[f"{U0}::0"])) is not None
+        with pytest.raises(grpc.RpcError) as e:
+            ch.unary_unary("/v1beta1.DevicePlugin/NoSuchMethod", request_serializer=lambda m: m.SerializeToString(), response_deserializer=lambda b: b)(api.Empty())
+        assert e.value.code() == grpc.StatusCode.UNIMPLEMENTED
+
+
+def test_fail_requests_greater_than_one(tmp_path):
+    d = str(tmp_path)
+    kubelet = FakeKubelet(d)
+    kubelet.start()
+    daemon = Daemon(d, "version: v1\nsharing:\n  timeSlicing:\n    failRequestsGreaterThanOne: true\n    resources:\n    - name: nvidia.com/gpu\n      replicas: 4\n")
+    try:
+        assert kubelet.event.wait(10) and daemon.wait_serving(), daemon.logtext()
+        with kubelet.plugin_channel() as ch:
+            stub = api.DevicePluginStub(ch)
+            with pytest.raises(grpc.RpcError) as e:
+                stub.Allocate(api.AllocateRequest(container_requests=[api.ContainerAllocateRequest(devices_ids=[f"{U0}::0", f"{U1}::0"])]))
+            assert "maximum request size for shared resources is 1" in e.value.details()
+            ok = stub.Allocate(api.AllocateRequest(container_requests=[api.ContainerAllocateRequest(devices_ids=[f"{U1}::0"])]))
+            assert dict(ok.container_responses[0].envs) == {"NVIDIA_VISIBLE_DEVICES": U1}
+    finally:
+        daemon.stop()
+        kubelet.stop()
+
+
+def test_preferred_allocation_spreads_replicas_across_gpus(stack):
+    kubelet, daemon = stack
+    all_ids = [f"{U0}::{r}" for r in range(4)] + [f"{U1}::{r}" for r in range(4)]
+    with kubelet.plugin_channel() as ch:
+        stub = api.DevicePluginStub(ch)
+        resp = stub.GetPreferredAllocation(api.PreferredAllocationRequest(container_requests=[
+            api.ContainerPreferredAllocationRequest(available_deviceIDs=all_ids, allocation_size=2)]))
+        got = list(resp.container_responses[0].deviceIDs)
+        assert {cfgmod.strip_replica(i) for i in got} == {U0, U1}
+        avail = [f"{U0}::3"] + [f"{U1}::{r}" for r in range(4)]
+        resp = stub.GetPreferredAllocation(api.PreferredAllocationRequest(container_requests=[
+            api.ContainerPreferredAllocationRequest(available_deviceIDs=avail, allocation_size=1)]))
+        assert cfgmod.strip_replica(resp.container_responses[0].deviceIDs[0]) == U1
+        with pytest.raises(grpc.RpcError) as e:
+            stub.GetPreferredAllocation(api.PreferredAllocationRequest(container_requests=[
+                api.ContainerPreferredAllocationRequest(available_deviceIDs=all_ids[:1], allocation_size=3)]))
+        assert "not enough available devices" in e.value.details()
+
+
+def test_preferred_allocation_matches_python_host_exactly(stack):
+    """distributed_alloc is deterministic in both hosts (ties by availability order): same picks."""
+    import random
+
+    from k3s_nvidia_b200.plugin import distributed_alloc
+
+    kubelet, daemon = stack
+    all_ids = [f"{U0}::{r}" for r in range(4)] + [f"{U1}::{r}" for r in range(4)]
+    rng = random.Random(11)
+    with kubelet.plugin_channel() as ch:
+        stub = api.DevicePluginStub(ch)
+        for _ in range(40):
+            avail = rng.sample(all_ids, rng.randint(1, 8))
+            must = rng.sample(avail, rng.randint(0, min(2, len(avail))))
+            size = rng.randint(len(must), len(avail))
+            resp = stub.GetPreferredAllocation(api.PreferredAllocationRequest(container_requests=[
+                api.ContainerPreferredAllocationRequest(available_deviceIDs=avail, must_include_deviceIDs=must, allocation_size=size)]))
+            assert list(resp.container_responses[0].deviceIDs) == distributed_alloc(all_ids, avail, must, size)
+
+
+def test_kubelet_restart_triggers_reregistration(stack):
+    kubelet, daemon = stack
+    n0 = len(kubelet.requests)
+    kubelet.stop()
+    time.sleep(0.2)
+    kubelet.event.clear()
+    kubelet.start()                              # socket re-created
+    assert kubelet.event.wait(10), "native plugin did not re-register after kubelet restart: " + daemon.logtext()
+    assert len(kubelet.requests) == n0 + 1
+    with kubelet.plugin_channel() as ch:
+        first = next(api.DevicePluginStub(ch).ListAndWatch(api.Empty()))
+        assert len(first.devices) == 8
+
+
+def test_many_calls_and_concurrent_streams_on_one_connection(stack):
+    """HPACK dynamic-table state and flow-control accounting must survive a long-lived connection."""
+    kubelet, daemon = stack
+    with kubelet.plugin_channel() as ch:
+        stub = api.DevicePluginStub(ch)
+        streams = [stub.ListAndWatch(api.Empty()) for _ in range(3)]
+        for s in streams:
+            assert len(next(s).devices) == 8
+        for i in range(300):
+            r = stub.Allocate(api.AllocateRequest(container_requests=[api.ContainerAllocateRequest(devices_ids=[f"{U0}::{i % 4}"])]))
+            assert dict(r.container_responses[0].envs) == {"NVIDIA_VISIBLE_DEVICES": U0}
+        daemon.push(1, 0, 0)                     # double-bit ECC on GPU 0: not an XID event -> skipped, no update
+        daemon.push(0, 1, 79)
+        for s in streams:
+            upd = next(s)
+            assert [d.health for d in upd.devices] == ["Healthy"] * 4 + ["Unhealthy"] * 4
+            s.cancel()
+
+
+CONFIG_CASES = [
+    "version: v1\n",
+    "version: v2\n",
+    "",
+    "version: v1\nflags:\n  migStrategy: mixed\n",
+    "version: v1\nflags:\n  migStrategy: sideways\n",
+    "version: v1\nflags:\n  plugin:\n    deviceIDStrategy: index\n    passDeviceSpecs: true\n",
+    "version: v1\nsharing:\n  timeSlicing:\n    renameByDefault: true\n    resources:\n    - name: nvidia.com/gpu\n      replicas: 2\n",
+    "version: v1\nsharing:\n  timeSlicing:\n    resources:\n      - name: gpu\n        replicas: 3\n        rename: gpu-shared\n",
+    "version: v1\nsharing:\n  timeSlicing:\n    resources:\n    - name: nvidia.com/gpu\n      replicas: 0\n",
+    "version: v1\nsharing:\n  timeSlicing:\n    resources:\n    - name: nvidia.com/gpu\n      replicas: four\n",
+    "version: v1\nsharing:\n  timeSlicing:\n    resources:\n    - name: nvidia.com/gpu\n      replicas: true\n",
+    "version: v1\nsharing:\n  timeSlicing:\n    resources:\n    - replicas: 2\n",
+    "version: v1\nsharing:\n  timeSlicing:\n    resources:\n    - name: amd.com/gpu\n      replicas: 2\n",
+    "version: v1\nsharing:\n  timeSlicing:\n    resources:\n    - name: nvidia.com/gpu\n      replicas: 2\n    - name: gpu\n      replicas: 3\n",
+    "version: v1\nsharing:\n  timeSlicing:\n    renameByDefault: maybe\n",
+    "version: v1\nsharing:\n  timeSlicing:\n    resources: 7\n",
+    "# comment first\nversion: 'v1'   # quoted\nflags: {}\nsharing:\n  timeSlicing:\n    resources: []\n",
+    "version: v1\nsharing:\n  timeSlicing:\n    failRequestsGreaterThanOne: yes\n    resources:\n    - {name: nvidia.com/gpu, replicas: 2}\n",
+    "---\nversion: v1\nflags:\n    migStrategy: \"single\"\nsharing:\n    timeSlicing:\n        resources:\n        -   name: nvidia.com/gpu\n            replicas: 0x10\n",
+]
+
+
+@pytest.mark.parametrize("i", range(len(CONFIG_CASES)))
+def test_config_document_parses_like_the_python_host(i, tmp_path):
+    """The native YAML subset + config rules against config.py (PyYAML) on the reference document, variants
+    of it and malformed documents: same fields, or an error where Python raises one."""
+    text = CONFIG_CASES[i]
+    path = tmp_path / "c.yaml"
+    path.write_text(text)
+    out = json.loads(subprocess.run([BIN, "--check-config", str(path)], capture_output=True, text=True, check=True).stdout)
+    try:
+        c = cfgmod.parse_plugin_config(text)
+    except Exception as e:  # noqa: BLE001 (ConfigError, or what a malformed document provokes)
+        assert out["ok"] is False, (text, out, e)
+        return
+    if not out["ok"]:
+        # the native reader refuses non-empty flow collections by design: that is the only allowed asymmetry
+        assert "flow collections" in out["error"], (text, out)
+        return
+    assert out["version"] == c.version and out["mig_strategy"] == c.mig_strategy
+    assert out["device_id_strategy"] == c.device_id_strategy and out["pass_device_specs"] == c.pass_device_specs
+    assert out["rename_by_default"] == c.time_slicing.rename_by_default
+    assert out["fail_requests_greater_than_one"] == c.time_slicing.fail_requests_greater_than_one
+    assert out["resources"] == [{"name": r.name, "replicas": r.replicas, "rename": r.rename} for r in c.time_slicing.resources]
+    assert (out["resource_name"], out["replicas"], out["is_shared"]) == (c.resource_name(), c.replicas(), c.is_shared())
+
+
+def test_reference_values_yaml_config_document(tmp_path):
+    """/root/reference/values.yaml:9-18 exactly as shipped (committed golden copy, sha256-pinned elsewhere)."""
+    path = tmp_path / "c.yaml"
+    path.write_text(VALUES.raw_configs["default"])
+    out = json.loads(subprocess.run([BIN, "--check-config", str(path)], capture_output=True, text=True, check=True).stdout)
+    assert out == {"ok": True, "version": "v1", "mig_strategy": "none", "device_list_strategy": "envvar", "device_id_strategy": "uuid",
+                   "pass_device_specs": False, "rename_by_default": False, "fail_requests_greater_than_one": False,
+                   "resources": [{"name": "nvidia.com/gpu", "replicas": 4, "rename": None}], "resource_name": "nvidia.com/gpu", "replicas": 4,
+                   "is_shared": True}
+
+
+def test_hpack_decoder_against_libnghttp2_deflater():
+    """The native HPACK decoder (static + dynamic table, Huffman) fed with header blocks produced by the
+    system libnghttp2's deflater (indexing + Huffman on), one decoder across all blocks."""
+    import ctypes as C
+    import ctypes.util
+    import random
+
+    name = ctypes.util.find_library("nghttp2")
+    if not name:
+        pytest.skip("libnghttp2 not on this box")
+    lib = C.CDLL(name)
+
+    class NV(C.Structure):
+        _fields_ = [("name", C.c_char_p), ("value", C.c_char_p), ("namelen", C.c_size_t), ("valuelen", C.c_size_t), ("flags", C.c_uint8)]
+
+    lib.nghttp2_hd_deflate_new.argtypes = [C.POINTER(C.c_void_p), C.c_size_t]
+    lib.nghttp2_hd_deflate_hd.restype = C.c_ssize_t
+    lib.nghttp2_hd_deflate_hd.argtypes = [C.c_void_p, C.c_char_p, C.c_size_t, C.POINTER(NV), C.c_size_t]
+    lib.nghttp2_hd_deflate_bound.restype = C.c_size_t
+    lib.nghttp2_hd_deflate_bound.argtypes = [C.c_void_p, C.POINTER(NV), C.c_size_t]
+    lib.nghttp2_hd_deflate_del.argtypes = [C.c_void_p]
+    defl = C.c_void_p()
+    assert lib.nghttp2_hd_deflate_new(C.byref(defl), 4096) == 0
+    rng = random.Random(7541)
+    names = [b":method", b":path", b":scheme", b":authority", b"content-type", b"te", b"user-agent", b"grpc-timeout", b"grpc-accept-encoding",
+             b"x-custom-" + bytes(rng.choice(b"abcdefghijklmnopqrstuvwxyz-") for _ in range(12)), b"accept-encoding", b"cookie"]
+    values = [b"POST", b"/v1beta1.DevicePlugin/Allocate", b"/v1beta1.DevicePlugin/ListAndWatch", b"http", b"localhost", b"application/grpc",
+              b"trailers", b"grpc-python/1.80.0 grpc-c/48.0.0 (linux; chttp2)", b"4999997u", b"identity, deflate, gzip", b""]
+    blocks, want = [], []
+    try:
+        for _ in range(300):
+            hs = []
+            for _ in range(rng.randint(1, 9)):
+                n = rng.choice(names)
+                v = rng.choice(values) if rng.random() < 0.7 else bytes(rng.randrange(32, 127) for _ in range(rng.randint(0, 80)))
+                hs.append((n, v))
+            if rng.random() < 0.1:
+                hs.append((b"x-big", bytes(rng.randrange(32, 127) for _ in range(3000))))      # forces evictions
+            arr = (NV * len(hs))(*[NV(n, v, len(n), len(v), 0) for n, v in hs])
+            buf = C.create_string_buffer(lib.nghttp2_hd_deflate_bound(defl, arr, len(hs)))
+            n = lib.nghttp2_hd_deflate_hd(defl, buf, len(buf), arr, len(hs))
+            assert n > 0
+            blocks.append(buf.raw[:n].hex())
+            want.append([[a.decode(), b.decode()] for a, b in hs])
+    finally:
+        lib.nghttp2_hd_deflate_del(defl)
+    out = subprocess.run([BIN, "--hpack-decode"], input="\n".join(blocks) + "\n", capture_output=True, text=True, check=True).stdout
+    got = [json.loads(line) for line in out.splitlines()]
+    assert got == want
+    # malformed blocks are rejected, not mis-decoded: index 0, index past the tables, truncated string, EOS inside Huffman data
+    bad = ["80", "ff7f", "0005616263", "0084ffffffff"]
+    out = subprocess.run([BIN, "--hpack-decode"], input="\n".join(bad) + "\n", capture_output=True, text=True, check=True).stdout
+    assert [json.loads(line) for line in out.splitlines()] == [{"error": "decode failed"}] * len(bad)
