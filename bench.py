@@ -24,7 +24,15 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
-os.environ["NCCL_DEBUG"] = os.environ.get("B200PROBE_NCCL_DEBUG", "WARN")   # NCCL_DEBUG=VERSION prints a banner on stdout; stdout carries ONE JSON line
+# stdout carries ONE JSON line: libraries that chat on fd 1 (NCCL prints its version banner there) are sent to
+# stderr, and the result line goes to a private duplicate of the original stdout.
+_RESULT_FD = os.dup(1)
+os.dup2(2, 1)
+
+
+def emit(line: dict) -> None:
+    os.write(_RESULT_FD, (json.dumps(line) + "\n").encode())
+
 
 GIB = 1 << 30
 METRIC = "health-probe HBM GB/s & NVLink GB/s vs peak per GPU at 1/2/4/8 B200"
@@ -156,7 +164,7 @@ def run_reference(args):
         "reference_path_nvml": nvml_poll_timing(o),
         "note": "the reference's own health path (passive NVML XID wait) moves 0 bytes; its timing is under reference_path_nvml",
     }
-    print(json.dumps(line))
+    emit(line)
     return 0
 
 
@@ -320,7 +328,7 @@ def run_ours(args):
         if nvlink:
             line["nvlink"] = nvlink
     if rank == 0:
-        print(json.dumps(line))
+        emit(line)
     D.barrier()
     p.close()
     if world > 1:
