@@ -1,8 +1,8 @@
 // Minimal HTTP/2 (RFC 9113) + gRPC framing over a unix-domain socket: exactly what the kubelet
 // device-plugin API needs (SURVEY.md §8b outer boundary) and nothing else.  No TLS, no push, no priorities.
 //
-//   Server side: one reader thread per connection; unary RPCs answered inline, server-streaming RPCs
-//   (ListAndWatch) on their own thread.  Send-side flow control is honoured (connection + stream windows);
+//   Server side: one reader thread per connection; every RPC is answered on its own worker thread (the
+//   reader must stay free for WINDOW_UPDATE frames).  Send-side flow control is honoured (connection + stream windows);
 //   received DATA is credited back immediately (messages on this API are a few KB).
 //   Client side: one blocking unary call per connection (Registration.Register).
 #pragma once
@@ -354,13 +354,16 @@ private:
         std::vector<std::string> msgs;
         if (!grpc_unframe(call->request_, &msgs) || msgs.size() != 1) { call->finish({INTERNAL, "malformed gRPC request body"}); return; }
         call->request_ = msgs[0];
-        if (it->second.streaming) {
-            Handler fn = it->second.fn;
-            std::lock_guard<std::mutex> l(mu_);
-            stream_threads_.emplace_back([fn, call] { fn(call); });
-        } else {
-            it->second.fn(call);
+        // Every RPC runs on its own thread: the reader must stay free to process WINDOW_UPDATE frames, or a
+        // response larger than the peer's flow-control window would wait on an update nobody reads.
+        Handler fn = it->second.fn;
+        auto done = std::make_shared<std::atomic<bool>>(false);
+        std::lock_guard<std::mutex> l(mu_);
+        for (size_t i = 0; i < workers_.size();) {                       // reap finished workers
+            if (workers_[i].done->load()) { workers_[i].t.join(); workers_.erase(workers_.begin() + (long)i); }
+            else ++i;
         }
+        workers_.push_back(Worker{std::thread([fn, call, done] { fn(call); done->store(true); }), done});
     }
     void goaway(uint32_t code) {
         write_frame(GOAWAY, 0, 0, u32be(0x7fffffff) + u32be(code));
@@ -374,9 +377,9 @@ private:
     }
     void join_streams() {
         cancel_all();
-        std::vector<std::thread> ts;
-        { std::lock_guard<std::mutex> l(mu_); ts.swap(stream_threads_); }
-        for (auto& t : ts) if (t.joinable()) t.join();
+        std::vector<Worker> ws;
+        { std::lock_guard<std::mutex> l(mu_); ws.swap(workers_); }
+        for (auto& w : ws) if (w.t.joinable()) w.t.join();
     }
 
     std::atomic<int> fd_;
@@ -390,7 +393,8 @@ private:
     int64_t peer_max_frame_ = 16384;
     hpack::Decoder dec_;
     std::map<uint32_t, std::shared_ptr<ServerCall>> calls_;
-    std::vector<std::thread> stream_threads_;
+    struct Worker { std::thread t; std::shared_ptr<std::atomic<bool>> done; };
+    std::vector<Worker> workers_;
 };
 
 inline bool ServerCall::send(const std::string& msg) {

@@ -370,3 +370,152 @@ def test_hpack_decoder_against_libnghttp2_deflater():
     bad = ["80", "ff7f", "0005616263", "0084ffffffff"]
     out = subprocess.run([BIN, "--hpack-decode"], input="\n".join(bad) + "\n", capture_output=True, text=True, check=True).stdout
     assert [json.loads(line) for line in out.splitlines()] == [{"error": "decode failed"}] * len(bad)
+
+
+def test_flow_control_large_device_list_and_large_unary_response(tmp_path):
+    """16 GPUs x 128 replicas = 2048 advertised devices: the ListAndWatch message (~110 KB) and a preferred
+    allocation of 1500 IDs both exceed the 65,535-byte initial HTTP/2 windows, so DATA has to be cut into
+    frames and wait for the peer's WINDOW_UPDATEs."""
+    d = str(tmp_path)
+    kubelet = FakeKubelet(d)
+    kubelet.start()
+    daemon = Daemon(d, "version: v1\nsharing:\n  timeSlicing:\n    resources:\n    - name: nvidia.com/gpu\n      replicas: 128\n",
+                    extra_env={"MOCK_NVML_DEVICES": "16"})
+    try:
+        assert kubelet.event.wait(10) and daemon.wait_serving(), daemon.logtext()
+        with kubelet.plugin_channel() as ch:
+            stub = api.DevicePluginStub(ch)
+            first = next(stub.ListAndWatch(api.Empty()))
+            ids = [x.ID for x in first.devices]
+            assert len(ids) == 2048 and len(set(ids)) == 2048 and first.ByteSize() > 100_000
+            assert ids[:2] == ["GPU-b2000000-0000-4000-8000-000000000000::0", "GPU-b2000000-0000-4000-8000-000000000000::1"]
+            resp = stub.GetPreferredAllocation(api.PreferredAllocationRequest(container_requests=[
+                api.ContainerPreferredAllocationRequest(available_deviceIDs=ids, allocation_size=1500)]))
+            got = list(resp.container_responses[0].deviceIDs)
+            assert len(got) == 1500 and len(set(got)) == 1500 and set(got) <= set(ids)
+            per_gpu = {}
+            for i in got:
+                per_gpu[cfgmod.strip_replica(i)] = per_gpu.get(cfgmod.strip_replica(i), 0) + 1
+            assert max(per_gpu.values()) - min(per_gpu.values()) <= 1          # spread evenly over the 16 GPUs
+            daemon.push(0, 3, 79)
+            stream = stub.ListAndWatch(api.Empty())
+            seen = next(stream)
+            if all(x.health == "Healthy" for x in seen.devices):
+                seen = next(stream)
+            assert sum(x.health == "Unhealthy" for x in seen.devices) == 128
+            stream.cancel()
+    finally:
+        daemon.stop()
+        kubelet.stop()
+
+
+def test_garbage_on_the_socket_does_not_take_the_daemon_down(stack):
+    import socket
+
+    kubelet, daemon = stack
+    path = os.path.join(daemon.dir, "nvidia-gpu.sock")
+    payloads = [b"GET / HTTP/1.1\r\nHost: x\r\n\r\n", b"\x00" * 64, os.urandom(4096),
+                b"PRI * HTTP/2.0\r\n\r\nSM\r\n\r\n" + b"\x00\x00\x05\x01\x04\x00\x00\x00\x01" + b"\xff\xff\xff\xff\xff",      # HEADERS with a bad HPACK block
+                b"PRI * HTTP/2.0\r\n\r\nSM\r\n\r\n" + b"\xff\xff\xff\x00\x00\x00\x00\x00\x01",                                   # 16 MiB frame announced, nothing sent
+                b"PRI * HTTP/2.0\r\n\r\nSM\r\n\r\n" + b"\x00\x00\x04\x08\x00\x00\x00\x00\x00" + b"\x00\x00\x00\x00" * 1]
+    for p in payloads:
+        s = socket.socket(socket.AF_UNIX, socket.SOCK_STREAM)
+        s.settimeout(2)
+        s.connect(path)
+        try:
+            s.sendall(p)
+            try:
+                s.recv(65536)
+            except (socket.timeout, ConnectionError):
+                pass
+        except (BrokenPipeError, ConnectionError):
+            pass
+        finally:
+            s.close()
+    assert daemon.proc.poll() is None, daemon.logtext()
+    with kubelet.plugin_channel() as ch:
+        assert len(next(api.DevicePluginStub(ch).ListAndWatch(api.Empty())).devices) == 8
+
+
+def test_yaml_subset_differential_against_pyyaml(tmp_path):
+    """Randomly generated plugin-config documents (block style, varied indentation, quoting, comments, booleans
+    in YAML 1.1 spellings, list items at the parent's indentation or deeper): the native reader must accept and
+    reject exactly what config.py over PyYAML does, with the same resulting fields."""
+    import random
+
+    rng = random.Random(20260921)
+
+    def scalar(v):
+        if isinstance(v, bool):
+            return rng.choice(["true", "True", "yes", "on"] if v else ["false", "False", "no", "off"])
+        if isinstance(v, int):
+            return rng.choice([str(v), str(v), hex(v)]) if v >= 0 else str(v)
+        q = rng.random()
+        return f'"{v}"' if q < 0.25 else f"'{v}'" if q < 0.5 else v
+
+    def comment():
+        return rng.choice(["", "", "", "  # note", " #x"])
+
+    docs = []
+    for _ in range(250):
+        ind = rng.choice([1, 2, 4])
+        sp = " " * ind
+        lines = []
+        if rng.random() < 0.2:
+            lines.append("# plugin configuration")
+        if rng.random() < 0.15:
+            lines.append("---")
+        version = rng.choice(["v1"] * 8 + ["v2", "1"])
+        lines.append(f"version: {scalar(version)}{comment()}")
+        if rng.random() < 0.6:
+            lines.append("flags:" + comment())
+            if rng.random() < 0.8:
+                lines.append(f"{sp}migStrategy: {scalar(rng.choice(['none', 'none', 'single', 'mixed', 'both']))}")
+            if rng.random() < 0.4:
+                lines.append(f"{sp}plugin:")
+                lines.append(f"{sp}{sp}deviceIDStrategy: {scalar(rng.choice(['uuid', 'index', 'serial']))}")
+                if rng.random() < 0.5:
+                    lines.append(f"{sp}{sp}passDeviceSpecs: {scalar(rng.random() < 0.5)}")
+        if rng.random() < 0.85:
+            lines.append("sharing:")
+            lines.append(f"{sp}timeSlicing:")
+            if rng.random() < 0.5:
+                lines.append(f"{sp}{sp}renameByDefault: {scalar(rng.random() < 0.5) if rng.random() < 0.9 else 'perhaps'}")
+            if rng.random() < 0.5:
+                lines.append(f"{sp}{sp}failRequestsGreaterThanOne: {scalar(rng.random() < 0.5)}")
+            if rng.random() < 0.9:
+                lines.append(f"{sp}{sp}resources:" + comment())
+                item_ind = sp * 2 + (sp if rng.random() < 0.5 else "")
+                for _ in range(rng.randint(0, 3)):
+                    name = rng.choice(["nvidia.com/gpu", "gpu", "nvidia.com/mig-1g.10gb", "amd.com/gpu", "nvidia.com/" + "x" * 60])
+                    reps = rng.choice([1, 2, 4, 8, 0, -1, "four", True])
+                    dash_gap = " " * rng.choice([1, 1, 3])
+                    fields = [("name", scalar(name)), ("replicas", scalar(reps))]
+                    if rng.random() < 0.3:
+                        fields.append(("rename", scalar(rng.choice(["gpu-shared", "nvidia.com/gpu.shared"]))))
+                    if rng.random() < 0.2:
+                        fields = fields[1:]            # missing name
+                    rng.shuffle(fields)
+                    lines.append(f"{item_ind}-{dash_gap}{fields[0][0]}: {fields[0][1]}{comment()}")
+                    for k, v in fields[1:]:
+                        lines.append(f"{item_ind} {dash_gap}{k}: {v}")
+        docs.append("\n".join(lines) + ("\n" if rng.random() < 0.9 else ""))
+
+    agree_ok = agree_err = 0
+    for i, text in enumerate(docs):
+        path = tmp_path / f"c{i}.yaml"
+        path.write_text(text)
+        out = json.loads(subprocess.run([BIN, "--check-config", str(path)], capture_output=True, text=True, check=True).stdout)
+        try:
+            c = cfgmod.parse_plugin_config(text)
+        except Exception:  # noqa: BLE001
+            assert out["ok"] is False, (text, out)
+            agree_err += 1
+            continue
+        assert out["ok"] is True, (text, out)
+        assert (out["version"], out["mig_strategy"], out["device_id_strategy"], out["pass_device_specs"]) == \
+            (c.version, c.mig_strategy, c.device_id_strategy, c.pass_device_specs), text
+        assert out["rename_by_default"] == c.time_slicing.rename_by_default and out["fail_requests_greater_than_one"] == c.time_slicing.fail_requests_greater_than_one
+        assert out["resources"] == [{"name": r.name, "replicas": r.replicas, "rename": r.rename} for r in c.time_slicing.resources], text
+        agree_ok += 1
+    assert agree_ok > 30 and agree_err > 30, (agree_ok, agree_err)       # the generator exercises both outcomes
