@@ -3,8 +3,8 @@
 // NOT COMPILED IN THIS REPOSITORY'S CI: the build image has no Go toolchain (`go version` -> not
 // found) and no network to fetch one.  This file is what a maintainer of the NVIDIA
 // k8s-device-plugin (installed by /root/reference/README.md:116) would add under internal/ to call
-// the probe from the plugin's resource manager; the Python host (k3s-nvidia_b200/plugin.py) is the
-// twin that runs and is tested here.  See INTEGRATION.md.
+// the probe from the plugin's resource manager; the C++ host (host/cpp) and its Python twin
+// (k3s-nvidia_b200/plugin.py) are what runs and is tested here.  See INTEGRATION.md.
 package b200probe
 
 /*
@@ -172,4 +172,56 @@ func GEMM(idx, m, n, k int) (tflops float64, verified bool, err error) {
 	var res C.b200probe_gemm_result_t
 	err = check(C.b200probe_gemm(C.int(idx), &cfg, &res))
 	return float64(res.tflops_median), res.verified == 1, err
+}
+
+// NVLinkStatus mirrors b200probe_nvlink_status_t: the passive NVML view of the links (state per link,
+// fabric registration + health mask, DATA/RAW throughput counters) that is correlated with NVLinkA2A.
+type NVLinkStatus struct {
+	LinksTotal, LinksActive  int
+	ActiveMask               uint32
+	FabricState, FabricStatus int
+	FabricHealthMask         uint32
+	DataTxKiB, DataRxKiB     uint64
+	RawTxKiB, RawRxKiB       uint64
+	CountersOK               bool
+}
+
+func NVLinkPassive(idx int) (NVLinkStatus, error) {
+	var st C.b200probe_nvlink_status_t
+	err := check(C.b200probe_nvlink_passive(C.int(idx), &st))
+	return NVLinkStatus{int(st.links_total), int(st.links_active), uint32(st.active_mask), int(st.fabric_state), int(st.fabric_status),
+		uint32(st.fabric_health_mask), uint64(st.data_tx_kib), uint64(st.data_rx_kib), uint64(st.raw_tx_kib), uint64(st.raw_rx_kib),
+		st.counters_ok == 1}, err
+}
+
+// HBMVerify is the probe's verdict pass on a device buffer of CUDA device `ordinal`: checksum of the
+// u32 words plus the number of words that differ from the closed-form pattern and the lowest such index.
+func HBMVerify(ordinal int, devPtr unsafe.Pointer, bytes uint64, seed uint32) (sum64 uint64, xor32 uint32, bad, first uint64, err error) {
+	runtime.LockOSThread()
+	defer runtime.UnlockOSThread()
+	var s, b, f C.uint64_t
+	var x C.uint32_t
+	err = check(C.b200probe_hbm_verify(C.int(ordinal), devPtr, C.uint64_t(bytes), C.uint32_t(seed), &s, &x, &b, &f))
+	return uint64(s), uint32(x), uint64(b), uint64(f), err
+}
+
+// HostAlloc returns page-locked host memory for HBMCopyHost (C-owned: release with HostFree, never the Go GC).
+func HostAlloc(bytes uint64) (unsafe.Pointer, error) {
+	var p unsafe.Pointer
+	err := check(C.b200probe_host_alloc(C.uint64_t(bytes), &p))
+	return p, err
+}
+
+func HostFree(p unsafe.Pointer) error { return check(C.b200probe_host_free(p)) }
+
+// HBMCopyHost round-trips src -> device -> dst through the copy kernel (pipelined over chunks) and
+// returns the checksum of what landed on the device.  src and dst must be C memory (HostAlloc) or
+// pinned Go memory (runtime.Pinner): cgo forbids passing Go pointers that the callee keeps using.
+func HBMCopyHost(ordinal int, src, dst unsafe.Pointer, bytes uint64) (sum64 uint64, xor32 uint32, err error) {
+	runtime.LockOSThread()
+	defer runtime.UnlockOSThread()
+	var s C.uint64_t
+	var x C.uint32_t
+	err = check(C.b200probe_hbm_copy_host(C.int(ordinal), src, dst, C.uint64_t(bytes), &s, &x))
+	return uint64(s), uint32(x), err
 }
