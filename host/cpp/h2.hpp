@@ -167,11 +167,13 @@ struct Route { Handler fn; bool streaming; };
 class Connection {
 public:
     Connection(int fd, const std::map<std::string, Route>* routes) : fd_(fd), routes_(routes) {}
-    ~Connection() { close_fd(); join_streams(); }
+    // The descriptor is closed only here, after the reader thread was joined by the owner and the workers by
+    // join_streams(): closing a descriptor another thread is blocked on is a race (and a reuse hazard).
+    ~Connection() { close_fd(); join_streams(); const int fd = fd_.exchange(-1); if (fd >= 0) ::close(fd); }
 
+    // Any thread: wake everything that waits on this connection and make further I/O fail.  Does not close.
     void close_fd() {
-        int fd = fd_.exchange(-1);
-        if (fd >= 0) { ::shutdown(fd, SHUT_RDWR); ::close(fd); }
+        if (!shut_.exchange(true)) { const int fd = fd_.load(); if (fd >= 0) ::shutdown(fd, SHUT_RDWR); }
         { std::lock_guard<std::mutex> l(mu_); dead_ = true; }
         cv_.notify_all();
     }
@@ -187,7 +189,7 @@ public:
         if (!read_all(fd, pre, 24) || memcmp(pre, kPreface, 24) != 0) return;
         Frame f;
         uint32_t continuing = 0;
-        while ((fd = fd_.load()) >= 0 && read_frame(fd, &f)) {
+        while (!shut_.load() && read_frame(fd, &f)) {
             if (continuing && (f.type != CONTINUATION || f.stream != continuing)) { goaway(1); break; }
             switch (f.type) {
                 case SETTINGS:
@@ -275,7 +277,7 @@ public:
         const std::string bytes = frame_bytes(type, flags, stream, payload);
         std::lock_guard<std::mutex> l(wmu_);
         const int fd = fd_.load();
-        return fd >= 0 && write_all(fd, bytes.data(), bytes.size());
+        return fd >= 0 && !shut_.load() && write_all(fd, bytes.data(), bytes.size());
     }
 
     // DATA under flow control; blocks while the peer's windows are closed.  false = connection or stream gone.
@@ -383,6 +385,7 @@ private:
     }
 
     std::atomic<int> fd_;
+    std::atomic<bool> shut_{false};
     std::atomic<bool> finished_{false};
     const std::map<std::string, Route>* routes_;
     std::mutex mu_, wmu_;
@@ -444,9 +447,10 @@ public:
     }
     void stop() {
         stopping_ = true;
-        int fd = lfd_.exchange(-1);
-        if (fd >= 0) { ::shutdown(fd, SHUT_RDWR); ::close(fd); }
+        const int lfd = lfd_.load();
+        if (lfd >= 0) ::shutdown(lfd, SHUT_RDWR);           // wakes the acceptor's poll; closed after it has exited
         if (acceptor_.joinable()) acceptor_.join();
+        if (lfd_.exchange(-1) >= 0) ::close(lfd);
         std::vector<std::shared_ptr<Connection>> conns;
         std::vector<std::thread> ts;
         { std::lock_guard<std::mutex> l(mu_); conns.swap(conns_); ts.swap(threads_); }

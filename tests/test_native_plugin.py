@@ -18,7 +18,7 @@ from k3s_nvidia_b200 import config as cfgmod
 from test_plugin import FakeKubelet, U0, U1
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-BIN = os.path.join(ROOT, "host", "cpp", "build", "b200-device-plugin")
+BIN = os.environ.get("B200_NATIVE_BIN") or os.path.join(ROOT, "host", "cpp", "build", "b200-device-plugin")
 G = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "golden.json")))
 VALUES = cfgmod.parse_helm_values(G["reference_inputs"]["values.yaml"]["text"])
 
@@ -67,6 +67,8 @@ class Daemon:
             except subprocess.TimeoutExpired:
                 self.proc.kill()
         self.log.close()
+        text = self.logtext()                # sanitizer builds (make -C host/cpp asan tsan) report on stderr
+        assert "Sanitizer" not in text and "runtime error" not in text, text[-4000:]
 
     def logtext(self):
         return open(os.path.join(self.dir, "daemon.log")).read()
