@@ -30,6 +30,7 @@
 // Roofline: NVLink bound.  Algorithmic bytes per GPU per direction: (G-1)*S payload bytes.
 #include <cuda_runtime.h>
 #include <dlfcn.h>
+#include <pthread.h>
 
 #include <algorithm>
 #include <vector>
@@ -432,22 +433,27 @@ uint32_t b200probe_a2a_chunk_seed(uint32_t seed, int src, int dst) { return chun
 
 int b200probe_enable_peer_access(const int* ordinals, int g) {
     if (!ordinals || g < 1 || g > kMaxWorld) return B200PROBE_EINVAL;
+    static pthread_mutex_t mu = PTHREAD_MUTEX_INITIALIZER;
+    static bool enabled[B200PROBE_MAX_DEVICES][B200PROBE_MAX_DEVICES];      // per process: asking twice is an API error, so remember
+    struct Lock { pthread_mutex_t* m; explicit Lock(pthread_mutex_t* x) : m(x) { pthread_mutex_lock(m); } ~Lock() { pthread_mutex_unlock(m); } } lock(&mu);
     for (int i = 0; i < g; ++i) {
         b200::DevProps props;
         int rc = b200::device_props(ordinals[i], &props);
         if (rc) return rc;
+        if (ordinals[i] < 0 || ordinals[i] >= B200PROBE_MAX_DEVICES) return B200PROBE_ERANGE;
         B200_CUDA_TRY(cudaSetDevice(ordinals[i]));
         for (int j = 0; j < g; ++j) {
-            if (i == j) continue;
+            if (i == j || ordinals[j] < 0 || ordinals[j] >= B200PROBE_MAX_DEVICES || enabled[ordinals[i]][ordinals[j]]) continue;
             int can = 0;
             B200_CUDA_TRY(cudaDeviceCanAccessPeer(&can, ordinals[i], ordinals[j]));
             if (!can) { b200::set_error("no peer access %d -> %d", ordinals[i], ordinals[j]); return B200PROBE_ENOPEER; }
             cudaError_t e = cudaDeviceEnablePeerAccess(ordinals[j], 0);
-            if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) {
+            if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) {       // "already": another library in this process (torch) got there first
                 b200::set_error("cudaDeviceEnablePeerAccess(%d -> %d): %s", ordinals[i], ordinals[j], cudaGetErrorString(e));
                 return b200::cuda_rc(e);
             }
-            cudaGetLastError();   // clear cudaErrorPeerAccessAlreadyEnabled
+            if (e != cudaSuccess) cudaGetLastError();
+            enabled[ordinals[i]][ordinals[j]] = true;
         }
     }
     return 0;
