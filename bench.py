@@ -231,7 +231,7 @@ def run_ours(args):
 
     # ---- e2e: the plugin-facing call, host cfg in -> host verdict out, every step -----------------
     e2e_steps = max(1, min(args.steps, 300))
-    kw = dict(min_bytes=nbytes, max_bytes=nbytes, modes=L.HBM_COPY, warmup=0, reps=1, verify=1, seed=seed)
+    kw = dict(min_bytes=nbytes, max_bytes=nbytes, modes=L.HBM_COPY, warmup=0, reps=1, verify=1, seed=seed, launches_per_rep=1)   # one verdict = one copy
     for _ in range(min(3, max(1, args.warmup))):
         p.hbm_sweep(nvml_index, **kw)
     torch.cuda.synchronize()

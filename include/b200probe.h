@@ -145,6 +145,9 @@ typedef struct b200probe_hbm_cfg {
     int      flush_l2;              /* 1 = overwrite a >L2 scratch between timed reps              */
     /* tuning (0 = built-in default) */
     int      stage_bytes, stages, warps_per_cta, ctas_per_sm;
+    int      launches_per_rep;      /* launches between the two events of one timed rep: 0 = about a
+                                       millisecond of work (the kernel's rate, not launch latency),
+                                       1 = single launches                                          */
 } b200probe_hbm_cfg_t;
 
 typedef struct b200probe_hbm_result {

@@ -85,6 +85,7 @@ class HbmCfg(C.Structure):
         ("stages", C.c_int),
         ("warps_per_cta", C.c_int),
         ("ctas_per_sm", C.c_int),
+        ("launches_per_rep", C.c_int),
     ]
 
 

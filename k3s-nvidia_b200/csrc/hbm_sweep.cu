@@ -689,17 +689,26 @@ int b200probe_hbm_sweep(int idx, const b200probe_hbm_cfg_t* cfg_in, b200probe_hb
             r.cache_resident = footprint <= (uint64_t)props.l2_bytes;
             if (mode != B200PROBE_HBM_READ && cfg.verify) B200_CUDA_TRY(cudaMemsetAsync(a.dst, 0, bytes, a.stream));
             B200_CUDA_TRY(cudaMemsetAsync(a.partials, 0, 32, a.stream));
+            // One timed rep = `inner` back-to-back launches between two events (about a millisecond of work), so
+            // the figure is the kernel's rate, not launch latency plus an event round trip; with an L2 flush
+            // between reps the launches are timed one at a time.
+            const double alg_bytes = (double)(mode == B200PROBE_HBM_COPY ? 2 * bytes : bytes);
+            const int inner = cfg.flush_l2 ? 1 : cfg.launches_per_rep > 0 ? std::min(cfg.launches_per_rep, 1024)
+                                                 : (int)std::max(1.0, std::min(64.0, std::floor(7.0e9 / alg_bytes + 0.5)));
             for (int it = -cfg.warmup; it < cfg.reps; ++it) {
                 if (cfg.flush_l2) B200_CUDA_TRY(cudaMemsetAsync(a.flush, it & 0xff, flush_bytes, a.stream));
                 if (it >= 0) B200_CUDA_TRY(cudaEventRecord(a.e0, a.stream));
-                if (mode == B200PROBE_HBM_READ) rc = b200probe_hbm_read(ordinal, a.src, bytes, (uint64_t*)a.partials, &cfg, a.stream);
-                else if (mode == B200PROBE_HBM_WRITE) rc = b200probe_hbm_fill(ordinal, a.dst, bytes, cfg.seed, &cfg, a.stream);
-                else rc = b200probe_hbm_copy(ordinal, a.src, a.dst, bytes, &cfg, a.stream);
-                if (rc) return rc;
+                for (int k = 0; k < (it >= 0 ? inner : 1); ++k) {
+                    if (mode == B200PROBE_HBM_READ) rc = b200probe_hbm_read(ordinal, a.src, bytes, (uint64_t*)a.partials, &cfg, a.stream);
+                    else if (mode == B200PROBE_HBM_WRITE) rc = b200probe_hbm_fill(ordinal, a.dst, bytes, cfg.seed, &cfg, a.stream);
+                    else rc = b200probe_hbm_copy(ordinal, a.src, a.dst, bytes, &cfg, a.stream);
+                    if (rc) return rc;
+                }
                 if (it >= 0) {
                     B200_CUDA_TRY(cudaEventRecord(a.e1, a.stream));
                     B200_CUDA_TRY(cudaEventSynchronize(a.e1));
                     B200_CUDA_TRY(cudaEventElapsedTime(&ms[it], a.e0, a.e1));
+                    ms[it] /= (float)inner;
                 }
             }
             r.ms_median = median(ms);

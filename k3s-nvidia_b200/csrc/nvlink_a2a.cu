@@ -267,6 +267,13 @@ __global__ void __launch_bounds__(kRingWarps * 32) a2a_stagger_kernel(XArgs a) {
     if (lane == 0) bulk_wait_all();
 }
 
+// ---- start gate (single-process probe): every device's exchange kernel is queued behind one of these and
+// all of them are released by ONE host store, so the exchanges start together instead of one launch overhead
+// apart (8 sequential launches are ~100 us of skew).  Spins on a word in mapped pinned host memory.
+__global__ void a2a_gate_kernel(const volatile uint32_t* gate, uint32_t want) {
+    while ((int32_t)(*gate - want) < 0) __nanosleep(100);       // released once the host word has reached this exchange's number
+}
+
 // ---- direct push: pattern in registers, 16-byte stores on the peer pointer --------------------------
 __global__ void __launch_bounds__(512) a2a_direct_kernel(XArgs a) {
     int p, sub;
@@ -293,11 +300,13 @@ __global__ void __launch_bounds__(512) a2a_direct_kernel(XArgs a) {
     }
 }
 
-// AUTO for the concurrent exchange.  The step barrier pays once a step is much longer than the launch skew
-// between ranks (tens of microseconds): at G = 8, S = 256 MiB it lifts 640-660 GB/s to 680; at S = 16 MiB
-// it costs 40 % (profiles/a2a_sync_r01_g8.txt).  With two ranks there is one peer and nothing to stagger.
-int auto_exchange_variant(int world, uint64_t S) {
-    return (world > 2 && S >= (64ull << 20)) ? B200PROBE_A2A_PUSH_SYNC : B200PROBE_A2A_PUSH_TMA;
+// AUTO for the concurrent exchange.  The step barrier pays once a step is much longer than the start skew
+// between ranks: free-running launches (one process per GPU, or sequential launches from one process) are
+// tens of microseconds apart, so the barrier wins from S = 256 MiB (G = 8: 680 vs 640-660 GB/s) and loses
+// below (S = 64 MiB: 583 vs 650; profiles/a2a_sweep_table_r01_g8_ungated.txt).  Behind the start gate of the
+// single-process probe the skew is gone and the barrier wins from 32 MiB.  Two ranks: nothing to stagger.
+int auto_exchange_variant(int world, uint64_t S, bool gated = false) {
+    return (world > 2 && S >= ((gated ? 32ull : 256ull) << 20)) ? B200PROBE_A2A_PUSH_SYNC : B200PROBE_A2A_PUSH_TMA;
 }
 
 int launch_exchange(int ordinal, int rank, int world, void* const* windows, uint64_t S, uint32_t seed, int variant, int ctas_per_peer,
@@ -402,6 +411,8 @@ struct PerDev {
 
 struct A2aCtx {
     std::vector<PerDev> d;
+    uint32_t* gate_host = nullptr;      // mapped pinned word the gate kernels spin on
+    uint32_t gate_epoch = 0;
     Nccl nccl;
     std::vector<ncclComm_t> comms;
     ~A2aCtx() {
@@ -416,6 +427,7 @@ struct A2aCtx {
             if (p.stream) cudaStreamDestroy(p.stream);
         }
         if (nccl.lib) dlclose(nccl.lib);
+        if (gate_host) cudaFreeHost(gate_host);
     }
 };
 
@@ -528,7 +540,8 @@ int b200probe_nvlink_a2a(const int* ordinals, int g, const b200probe_a2a_cfg_t* 
     out->verified = -1;
     if (pair_gbs) std::fill(pair_gbs, pair_gbs + g * g, 0.0);
     const bool nccl_mode = cfg.mode == B200PROBE_A2A_NCCL;
-    if (cfg.variant == B200PROBE_A2A_AUTO) cfg.variant = cfg.mode == B200PROBE_A2A_PEER_PAIR ? B200PROBE_A2A_PULL_TMA : auto_exchange_variant(g, cfg.bytes_per_pair);
+    const bool gated = !nccl_mode && cfg.mode == B200PROBE_A2A_PEER_ALL && !getenv("B200PROBE_A2A_NO_GATE");
+    if (cfg.variant == B200PROBE_A2A_AUTO) cfg.variant = cfg.mode == B200PROBE_A2A_PEER_PAIR ? B200PROBE_A2A_PULL_TMA : auto_exchange_variant(g, cfg.bytes_per_pair, gated);
     if (cfg.variant == B200PROBE_A2A_MIX_TMA && cfg.mode == B200PROBE_A2A_PEER_PAIR) cfg.variant = B200PROBE_A2A_PULL_TMA;
     const bool pull = !nccl_mode && cfg.variant == B200PROBE_A2A_PULL_TMA;
     const bool mix = !nccl_mode && cfg.variant == B200PROBE_A2A_MIX_TMA;
@@ -554,6 +567,10 @@ int b200probe_nvlink_a2a(const int* ordinals, int g, const b200probe_a2a_cfg_t* 
     }
     void* windows[kMaxWorld] = {nullptr};
     for (int i = 0; i < g; ++i) windows[i] = ctx.d[i].window;
+    if (gated) {
+        B200_CUDA_TRY(cudaHostAlloc((void**)&ctx.gate_host, 64, cudaHostAllocPortable | cudaHostAllocMapped));
+        *ctx.gate_host = 0;
+    }
 
     if (nccl_mode) {
         rc = load_nccl(&ctx.nccl);
@@ -571,8 +588,19 @@ int b200probe_nvlink_a2a(const int* ordinals, int g, const b200probe_a2a_cfg_t* 
     };
     // one all-pairs exchange; per-device elapsed ms into t[]
     auto exchange = [&](bool timed, std::vector<double>* t) -> int {
+        const uint32_t release = ++ctx.gate_epoch;
+        struct Release {                                   // whatever path leaves this function, no gate kernel is left spinning
+            uint32_t* word; uint32_t v;
+            ~Release() { if (word) __atomic_store_n(word, v, __ATOMIC_RELEASE); }
+        } release_guard{gated ? ctx.gate_host : nullptr, release};
         for (int i = 0; i < g; ++i) {
             B200_CUDA_TRY(cudaSetDevice(ctx.d[i].ordinal));
+            if (gated) {
+                uint32_t* dev_gate = nullptr;
+                B200_CUDA_TRY(cudaHostGetDevicePointer((void**)&dev_gate, ctx.gate_host, 0));
+                a2a_gate_kernel<<<1, 1, 0, ctx.d[i].stream>>>(dev_gate, release);
+                B200_CUDA_TRY(cudaGetLastError());
+            }
             if (timed) B200_CUDA_TRY(cudaEventRecord(ctx.d[i].e0, ctx.d[i].stream));
             if (!nccl_mode) {
                 // -2: the local slot is HBM traffic, not NVLink: kept out of the timed exchange
@@ -581,6 +609,7 @@ int b200probe_nvlink_a2a(const int* ordinals, int g, const b200probe_a2a_cfg_t* 
                 if (timed) B200_CUDA_TRY(cudaEventRecord(ctx.d[i].e1, ctx.d[i].stream));
             }
         }
+        if (gated) __atomic_store_n(ctx.gate_host, release, __ATOMIC_RELEASE);      // every device's exchange starts now
         if (nccl_mode) {
             NCCL_TRY(ctx.nccl, ctx.nccl.GroupStart());
             for (int i = 0; i < g; ++i)

@@ -178,10 +178,10 @@ class Probe:
     # -- HBM -------------------------------------------------------------------------------------
     def hbm_sweep(self, idx: int = 0, *, min_bytes=None, max_bytes=None, modes=None, warmup=None, reps=None,
                   seed=None, variant=None, verify=1, flush_l2=None, stage_bytes=None, stages=None,
-                  warps_per_cta=None, ctas_per_sm=None) -> List[HbmPoint]:
+                  warps_per_cta=None, ctas_per_sm=None, launches_per_rep=None) -> List[HbmPoint]:
         cfg = _hbm_cfg(min_bytes=min_bytes, max_bytes=max_bytes, modes=modes, warmup=warmup, reps=reps, seed=seed,
                        variant=variant, verify=verify, flush_l2=flush_l2, stage_bytes=stage_bytes, stages=stages,
-                       warps_per_cta=warps_per_cta, ctas_per_sm=ctas_per_sm)
+                       warps_per_cta=warps_per_cta, ctas_per_sm=ctas_per_sm, launches_per_rep=launches_per_rep)
         cap = 128
         out = (L.HbmResult * cap)()
         n = C.c_int()

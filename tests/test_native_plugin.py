@@ -521,3 +521,70 @@ def test_yaml_subset_differential_against_pyyaml(tmp_path):
         assert out["resources"] == [{"name": r.name, "replicas": r.replicas, "rename": r.rename} for r in c.time_slicing.resources], text
         agree_ok += 1
     assert agree_ok > 30 and agree_err > 30, (agree_ok, agree_err)       # the generator exercises both outcomes
+
+
+def _kube_schedule_and_allocate(pod_spec, node_labels, stub, advertised, in_use):
+    """What scheduler + kubelet do with a pod on one node, reduced to the device-plugin path: nodeSelector
+    against the node's labels, count of free units of the extended resource, GetPreferredAllocation, Allocate."""
+    for k, v in (pod_spec.get("nodeSelector") or {}).items():
+        if node_labels.get(k) != v:
+            return None, f"node(s) didn't match Pod's node affinity/selector ({k}={node_labels.get(k)!r}, wants {v!r})"
+    want = int(pod_spec["containers"][0]["resources"]["limits"]["nvidia.com/gpu"])
+    free = [d.ID for d in advertised if d.health == "Healthy" and d.ID not in in_use]
+    if len(free) < want:
+        return None, "Insufficient nvidia.com/gpu"
+    pref = stub.GetPreferredAllocation(api.PreferredAllocationRequest(container_requests=[
+        api.ContainerPreferredAllocationRequest(available_deviceIDs=free, allocation_size=want)]))
+    ids = list(pref.container_responses[0].deviceIDs)
+    resp = stub.Allocate(api.AllocateRequest(container_requests=[api.ContainerAllocateRequest(devices_ids=ids)]))
+    in_use.update(ids)
+    return (ids, dict(resp.container_responses[0].envs)), None
+
+
+def test_config5_jellyfin_is_scheduled_onto_a_probe_healthy_node_via_allocate(stack, tmp_path):
+    """BASELINE config 5: the reference's jellyfin Deployment (/root/reference/jellyfin.yaml, golden copy) with
+    deploy/jellyfin-gated.patch.yaml merged in lands on the node only while the probe's gate label is true, and
+    its container gets NVIDIA_VISIBLE_DEVICES=<uuid> from Allocate; four replicas fit one GPU (values.yaml:18)."""
+    import yaml
+
+    from k3s_nvidia_b200 import labels as L
+
+    kubelet, daemon = stack
+    docs = list(yaml.safe_load_all(G["reference_inputs"]["jellyfin.yaml"]["text"]))
+    deployment = next(d for d in docs if d["kind"] == "Deployment")
+    patch = yaml.safe_load(open(os.path.join(ROOT, "deploy", "jellyfin-gated.patch.yaml")))
+    pod = dict(deployment["spec"]["template"]["spec"])
+    pod.update(patch["spec"]["template"]["spec"])                     # strategic merge of the one added key
+    assert pod["runtimeClassName"] == "nvidia" and pod["nodeSelector"] == {"nvidia.com/b200probe.healthy": "true"}
+
+    def node_labels(healthy):
+        lab = {"nvidia.com/b200probe.hbm-healthy": "true" if healthy else "false", "nvidia.com/b200probe.gemm-healthy": "true"}
+        lab.update(L.gate_label(lab))
+        path = L.write_feature_file(lab, str(tmp_path / "features.d"))
+        return {**L.parse_feature_file(open(path).read()), "nvidia.com/gpu.present": "true"}     # what NFD turns the file into
+
+    with kubelet.plugin_channel() as ch:
+        stub = api.DevicePluginStub(ch)
+        stream = stub.ListAndWatch(api.Empty())
+        advertised = list(next(stream).devices)
+        in_use = set()
+        got, why = _kube_schedule_and_allocate(pod, node_labels(False), stub, advertised, in_use)
+        assert got is None and "didn't match" in why                  # probe failed: the pod stays Pending
+        got, why = _kube_schedule_and_allocate(pod, node_labels(True), stub, advertised, in_use)
+        assert why is None
+        ids, envs = got
+        assert len(ids) == 1 and ids[0].split("::")[0] in (U0, U1) and envs == {"NVIDIA_VISIBLE_DEVICES": ids[0].split("::")[0]}
+        # 2 GPUs x 4 replicas: seven more single-GPU pods fit, spread 4 + 4 over the two GPUs; the ninth is refused
+        for _ in range(7):
+            got, why = _kube_schedule_and_allocate(pod, node_labels(True), stub, advertised, in_use)
+            assert why is None
+        per_gpu = {}
+        for i in in_use:
+            per_gpu[i.split("::")[0]] = per_gpu.get(i.split("::")[0], 0) + 1
+        assert per_gpu == {U0: 4, U1: 4}
+        assert _kube_schedule_and_allocate(pod, node_labels(True), stub, advertised, in_use) == (None, "Insufficient nvidia.com/gpu")
+        # an XID on GPU 1 takes its four units out of the schedulable pool (ListAndWatch update)
+        daemon.push(0, 1, 79)
+        advertised = list(next(stream).devices)
+        assert sum(d.health == "Healthy" for d in advertised) == 4
+        stream.cancel()

@@ -1,3 +1,4 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests -m gpu -x -q 2>&1 | tail -12 | tee gpurun_out/pytest_gpu_2.txt
+timeout 300 python -m pytest tests/test_gpu_a2a.py tests/test_gpu_hbm.py -m gpu -x -q 2>&1 | tail -4
+timeout 300 python tools/sweep_tables.py 2>&1 | tail -28
