@@ -27,7 +27,7 @@ namespace labels {
 static const char kPrefix[] = "nvidia.com/b200probe.";
 static const double kHbmNominal = 8000.0, kHbmMeasured = 6565.8;            // north_star's denominator; MEASURED_PEAKS.json hbm_gbs
 static const double kNvlinkNominal = 900.0;
-static const double kNvlinkHealthyPair = 692.0, kNvlinkHealthyBox = 673.0;  // profiles/a2a_tune_r01_2gpu.txt; profiles/a2a_sync_r01_g8.txt
+static const double kNvlinkHealthyPair = 692.0, kNvlinkHealthyBox = 700.0;  // profiles/a2a_tune_r01_2gpu.txt; profiles/a2a_sync_relaxed_r01_g8.txt
 static const double kGemmMeasured = 1670.2;
 
 using Labels = std::map<std::string, std::string>;
@@ -103,7 +103,7 @@ inline Labels nvlink_labels(const b200probe_a2a_result_t& rep, const std::vector
     Labels out;
     const int G = rep.g;
     bool ok = rep.verified != 0;
-    const double min_gbs = th.nvlink_min_gbs > 0 ? th.nvlink_min_gbs : 0.97 * (G <= 2 ? kNvlinkHealthyPair : kNvlinkHealthyBox);
+    const double min_gbs = th.nvlink_min_gbs > 0 ? th.nvlink_min_gbs : (G <= 2 ? 0.97 * kNvlinkHealthyPair : 0.96 * kNvlinkHealthyBox);
     double min_egress = 1e300;
     for (int g = 0; g < G; ++g) {
         out[key(g, "nvlink-egress-gbs")] = rint_str(rep.egress_gbs[g]);

@@ -203,7 +203,7 @@ int b200probe_host_free(void* ptr);
 #define B200PROBE_A2A_NCCL        2   /* grouped ncclSend/ncclRecv (the library leg, for contrast) */
 /* exchange kernels (cfg.variant) */
 #define B200PROBE_A2A_AUTO        0   /* one pair: PULL_TMA; concurrent exchange: PUSH_SYNC when G > 2 and
-                                         S >= 64 MiB (the barrier must outweigh launch skew), else PUSH_TMA */
+                                         S >= 64 MiB (128 MiB for free-running launches), else PUSH_TMA */
 #define B200PROBE_A2A_PULL_TMA    1   /* bulk-LOAD the peers' send chunks over NVLink: best one-way
                                          (756-781 GB/s), worse when both directions are loaded (626) */
 #define B200PROBE_A2A_PUSH_TMA    2   /* generate in shared memory, bulk-STORE into the peers: best
@@ -217,8 +217,8 @@ int b200probe_host_free(void* ptr);
                                          (r+t) mod G at step t: one source per destination at a time */
 
 #define B200PROBE_A2A_PUSH_SYNC    7  /* PUSH_STAGGER + a device-side barrier over all ranks before every
-                                         step (flags in the windows' sync pages, written over NVLink):
-                                         687 GB/s per direction at G = 8 vs 640-660 unsynchronised    */
+                                         step (relaxed flags in the windows' sync pages, written over
+                                         NVLink): 701 GB/s per direction at G = 8 vs 618-660 free-running */
 
 typedef struct b200probe_a2a_cfg {
     uint64_t bytes_per_pair;        /* S, multiple of 16; 0 = 256 MiB                              */

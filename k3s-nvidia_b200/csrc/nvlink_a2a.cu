@@ -12,14 +12,14 @@
 //               bulk-stores them into its own recv slots.  Best for ONE direction at a time (the
 //               pairwise matrix): 756-781 GB/s vs 699-712 for writes (profiles/p2p_pull_tune_r01.txt)
 //   AUTO        (default) PULL_TMA for an isolated pair; for the concurrent exchange PUSH_SYNC when G > 2
-//               and S >= 64 MiB, else PUSH_TMA
+//               and S >= 64 MiB (128 MiB without the start gate), else PUSH_TMA
 //   PUSH_DIRECT pattern generated in registers, 16-byte stores on the peer pointers
 //   PUSH_BUF    local send chunk bulk-loaded, bulk-stored to the peer
 //   PUSH_STAGGER PUSH_TMA, but the whole grid works on one peer at a time in the rotation (rank+t) mod G
 //   PUSH_SYNC   PUSH_STAGGER with a device-side barrier across ALL ranks before every step (flags in the
 //               4 KiB sync page that ends each window, written over NVLink): steps stay aligned, so every
-//               GPU sends to one peer and receives from one peer at any time.  687 GB/s per direction at
-//               G = 8 against 640-660 for the concurrent push (profiles/a2a_step_sync_r01_g8.txt)
+//               GPU sends to one peer and receives from one peer at any time.  701 GB/s per direction at
+//               G = 8, S = 256 MiB against 618-660 for the concurrent push (profiles/a2a_sync_relaxed_r01_g8.txt)
 //   MIX_TMA     every (src,dst) chunk is moved by BOTH ends at once: the first `split` bytes are pushed
 //               by src (PUSH_TMA), the rest pulled by dst (PULL_TMA), so each link direction carries
 //               posted writes and read responses side by side (B200PROBE_A2A_MIX_PCT = pushed share)
@@ -61,6 +61,7 @@ struct XArgs {
     uint64_t split;    // MIX_TMA: bytes [0,split) of every chunk are pushed by its source, [split,S) pulled by its destination
     int push_ctas;     // MIX_TMA: CTAs (of ctas_per_peer) in the push role
     uint32_t timeout_us;   // PUSH_SYNC: longest wait at a step barrier before the launch gives up synchronising
+    int sync_every;        // PUSH_SYNC: a barrier before steps 1, 1+k, 1+2k, ... (k = 1: every step)
 };
 
 // Sync page at window + 2*world*S (zeroed when the window is created).  flag[q] is written by rank q with a
@@ -204,11 +205,11 @@ __global__ void __launch_bounds__(kRingWarps * 32) a2a_stagger_kernel(XArgs a) {
     for (int t = (a.only_peer == -1 ? 0 : 1); t < a.world; ++t) {
         const int p = (a.rank + t) % a.world;
         if (a.only_peer >= 0 && p != a.only_peer) continue;
-        if (sync && t >= 1) {
+        if (sync && t >= 1 && (t - 1) % a.sync_every == 0) {
             // ---- barrier t-1 over every CTA of every rank: arrive locally, last arriver raises this rank's
             // flag on all ranks, then everyone polls its LOCAL sync page.  A wait longer than timeout_us gives
             // up synchronising for the rest of the launch (a peer that never launched must not hang the GPU).
-            const uint32_t b = (uint32_t)(t - 1), nb = (uint32_t)(a.world - 1);
+            const uint32_t b = (uint32_t)((t - 1) / a.sync_every), nb = (uint32_t)((a.world - 2) / a.sync_every + 1);
             const uint32_t target = epoch * 16u + b + 1u;
             __syncthreads();                    // every warp of this CTA has issued its stores of the step before
             if (threadIdx.x == 0) {
@@ -217,7 +218,9 @@ __global__ void __launch_bounds__(kRingWarps * 32) a2a_stagger_kernel(XArgs a) {
                     if (b + 1 == nb) { atomicExch(&mine->cnt, 0u); atomicExch(&mine->epoch, epoch + 1u); }   // last barrier of the launch
                     for (int q = 0; q < a.world; ++q) {
                         SyncPage* theirs = reinterpret_cast<SyncPage*>(a.peers.win[q] + 2ull * a.world * S);
-                        asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(&theirs->flag[a.rank]), "r"(target) : "memory");
+                        // a pacing signal, not a publication: relaxed.  (st.release.sys fences the SM's outstanding
+                        // stores first — with megabytes of bulk stores in flight that drained the pipeline at every step.)
+                        asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(&theirs->flag[a.rank]), "r"(target) : "memory");
                     }
                 }
             }
@@ -227,7 +230,7 @@ __global__ void __launch_bounds__(kRingWarps * 32) a2a_stagger_kernel(XArgs a) {
                 bool ok = false;
                 while (!ok) {
                     uint32_t v = target;
-                    if (lane < a.world) asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(&mine->flag[lane]) : "memory");
+                    if (lane < a.world) asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(&mine->flag[lane]) : "memory");
                     ok = __all_sync(0xffffffffu, (int32_t)(v - target) >= 0);
                     if (!ok) {
                         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
@@ -300,13 +303,13 @@ __global__ void __launch_bounds__(512) a2a_direct_kernel(XArgs a) {
     }
 }
 
-// AUTO for the concurrent exchange.  The step barrier pays once a step is much longer than the start skew
-// between ranks: free-running launches (one process per GPU, or sequential launches from one process) are
-// tens of microseconds apart, so the barrier wins from S = 256 MiB (G = 8: 680 vs 640-660 GB/s) and loses
-// below (S = 64 MiB: 583 vs 650; profiles/a2a_sweep_table_r01_g8_ungated.txt).  Behind the start gate of the
-// single-process probe the skew is gone and the barrier wins from 32 MiB.  Two ranks: nothing to stagger.
+// AUTO for the concurrent exchange.  With the relaxed-flag barrier a step barrier costs a few microseconds, so
+// keeping the steps aligned wins as soon as a step is long against the start skew between ranks: at G = 8
+// from S = 64 MiB behind the start gate of the single-process probe (681 vs 655 GB/s; 701 vs 618 at 256 MiB,
+// profiles/a2a_sync_relaxed_r01_g8.txt), one size later for free-running launches.  Below that the
+// concurrent push is as good or better (8 MiB: 604 vs 579).  Two ranks: one peer, nothing to stagger.
 int auto_exchange_variant(int world, uint64_t S, bool gated = false) {
-    return (world > 2 && S >= ((gated ? 32ull : 256ull) << 20)) ? B200PROBE_A2A_PUSH_SYNC : B200PROBE_A2A_PUSH_TMA;
+    return (world > 2 && S >= ((gated ? 64ull : 128ull) << 20)) ? B200PROBE_A2A_PUSH_SYNC : B200PROBE_A2A_PUSH_TMA;
 }
 
 int launch_exchange(int ordinal, int rank, int world, void* const* windows, uint64_t S, uint32_t seed, int variant, int ctas_per_peer,
@@ -352,6 +355,8 @@ int launch_exchange(int ordinal, int rank, int world, void* const* windows, uint
             if (variant == B200PROBE_A2A_PUSH_SYNC) {
                 grid = std::min(grid, props.sms);                                // the barrier needs every CTA resident (1 CTA/SM at this ring size)
                 a.timeout_us = 200000;
+                a.sync_every = 1;
+                if (const char* e = getenv("B200PROBE_A2A_SYNC_EVERY")) { int v = atoi(e); if (v >= 1 && v <= kMaxWorld) a.sync_every = v; }
                 if (const char* e = getenv("B200PROBE_A2A_SYNC_TIMEOUT_US")) { int v = atoi(e); if (v > 0) a.timeout_us = (uint32_t)v; }
             }
             B200_CUDA_TRY(cudaFuncSetAttribute(a2a_stagger_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
