@@ -166,6 +166,8 @@ struct Route { Handler fn; bool streaming; };
 
 class Connection {
 public:
+    static constexpr size_t kMaxConcurrentStreams = 100;     // advertised in SETTINGS and enforced
+    static constexpr size_t kMaxHeaderBlock = 64 * 1024;     // gRPC request headers are a few hundred bytes
     Connection(int fd, const std::map<std::string, Route>* routes) : fd_(fd), routes_(routes) {}
     // The descriptor is closed only here, after the reader thread was joined by the owner and the workers by
     // join_streams(): closing a descriptor another thread is blocked on is a race (and a reuse hazard).
@@ -183,8 +185,9 @@ public:
         char pre[24];
         int fd = fd_.load();
         if (fd < 0) return;
-        std::string settings;                                           // SETTINGS: MAX_CONCURRENT_STREAMS = 100
-        settings += (char)0; settings += (char)MAX_CONCURRENT_STREAMS; settings += u32be(100);
+        std::string settings;                                           // SETTINGS: MAX_CONCURRENT_STREAMS, MAX_HEADER_LIST_SIZE
+        settings += (char)0; settings += (char)MAX_CONCURRENT_STREAMS; settings += u32be((uint32_t)kMaxConcurrentStreams);
+        settings += (char)0; settings += (char)MAX_HEADER_LIST_SIZE; settings += u32be((uint32_t)kMaxHeaderBlock);
         if (!write_frame(SETTINGS, 0, 0, settings)) return;
         if (!read_all(fd, pre, 24) || memcmp(pre, kPreface, 24) != 0) return;
         Frame f;
@@ -217,16 +220,25 @@ public:
                     if (f.flags & PRIORITY_FLAG) off += 5;
                     if (off + pad > f.payload.size()) { goaway(1); return; }
                     std::shared_ptr<ServerCall> call;
+                    bool refused = false;
                     {
                         std::lock_guard<std::mutex> l(mu_);
                         auto it = calls_.find(f.stream);
-                        if (it == calls_.end()) {
+                        if (it == calls_.end() && calls_.size() >= kMaxConcurrentStreams) refused = true;
+                        else if (it == calls_.end()) {
                             call = std::make_shared<ServerCall>(this, f.stream, "");
                             call->send_window_ = peer_initial_window_;
                             calls_[f.stream] = call;
                         } else call = it->second;                         // trailers from a client: not used by gRPC requests
                     }
+                    if (refused) {
+                        // the block still has to pass through the HPACK decoder (it may update the dynamic table);
+                        // simplest correct answer for a peer that ignores our SETTINGS is to drop the connection
+                        goaway(7);                                            // REFUSED_STREAM
+                        return;
+                    }
                     call->header_block_.append(f.payload, off, f.payload.size() - off - pad);
+                    if (call->header_block_.size() > kMaxHeaderBlock) { goaway(11); return; }   // ENHANCE_YOUR_CALM
                     if (f.flags & END_STREAM) call->request_done_ = true;
                     if (f.flags & END_HEADERS) { if (!headers_complete(call)) return; }
                     else continuing = f.stream;
@@ -236,6 +248,7 @@ public:
                     std::shared_ptr<ServerCall> call = find(f.stream);
                     if (!call || continuing != f.stream) { goaway(1); return; }
                     call->header_block_ += f.payload;
+                    if (call->header_block_.size() > kMaxHeaderBlock) { goaway(11); return; }
                     if (f.flags & END_HEADERS) { continuing = 0; if (!headers_complete(call)) return; }
                     break;
                 }

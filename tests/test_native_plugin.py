@@ -588,3 +588,49 @@ def test_config5_jellyfin_is_scheduled_onto_a_probe_healthy_node_via_allocate(st
         advertised = list(next(stream).devices)
         assert sum(d.health == "Healthy" for d in advertised) == 4
         stream.cancel()
+
+
+def test_limits_are_enforced_without_hurting_well_behaved_clients(stack):
+    """A header block that never ends and a client that opens more streams than SETTINGS allows are cut off
+    (GOAWAY), and the daemon keeps serving others."""
+    import socket
+    import struct
+
+    kubelet, daemon = stack
+    path = os.path.join(daemon.dir, "nvidia-gpu.sock")
+
+    def frame(t, flags, stream, payload=b""):
+        return struct.pack(">I", len(payload))[1:] + bytes([t, flags]) + struct.pack(">I", stream) + payload
+
+    def talk(data):
+        s = socket.socket(socket.AF_UNIX, socket.SOCK_STREAM)
+        s.settimeout(3)
+        s.connect(path)
+        got = b""
+        try:
+            s.sendall(data)
+            while True:
+                chunk = s.recv(65536)
+                if not chunk:
+                    break
+                got += chunk
+        except (socket.timeout, ConnectionError, BrokenPipeError):
+            pass
+        finally:
+            s.close()
+        return got
+
+    pre = b"PRI * HTTP/2.0\r\n\r\nSM\r\n\r\n" + frame(4, 0, 0)
+    # HEADERS without END_HEADERS followed by 10 x 16 KiB CONTINUATION frames of literal headers
+    lit = b"\x00\x01a" + b"\x7f\xf1\x7e" + b"b" * 16368          # name "a", value of 16368 bytes (7-bit prefix integer 127 + 16241)
+    flood = pre + frame(1, 0, 1, lit[:16000]) + b"".join(frame(9, 0, 1, lit[:16000]) for _ in range(10))
+    got = talk(flood)
+    assert b"\x07\x00\x00\x00\x00\x00" in got        # a GOAWAY frame (type 7, stream 0) came back
+    # 150 streams opened and left half-open (no END_STREAM): refused once 100 are in flight
+    hdr = (b"\x83\x86\x44\x1e/v1beta1.DevicePlugin/Allocate" + b"\x41\x09localhost" + b"\x5f\x10application/grpc" + b"\x40\x02te\x08trailers")
+    many = pre + b"".join(frame(1, 4, 1 + 2 * i, hdr) for i in range(150))
+    got = talk(many)
+    assert b"\x07\x00\x00\x00\x00\x00" in got
+    assert daemon.proc.poll() is None
+    with kubelet.plugin_channel() as ch:
+        assert len(next(api.DevicePluginStub(ch).ListAndWatch(api.Empty())).devices) == 8
