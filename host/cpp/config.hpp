@@ -143,6 +143,41 @@ inline PluginConfig parse_plugin_config(const std::string& text) {
     return cfg;
 }
 
+// The Helm values file exactly as the reference ships it (/root/reference/values.yaml:1-18): gfd.enabled (:1-2),
+// runtimeClassName (:4), config.map.<name> = the plugin config documents as YAML block scalars (:6-18).
+struct HelmValues {
+    bool gfd_enabled = false;
+    std::string runtime_class_name;                                   // empty = unset
+    std::vector<std::pair<std::string, std::string>> raw_configs;      // name -> document text, file order
+    std::vector<std::pair<std::string, PluginConfig>> configs;
+
+    // "default" if present, else the only one, else the built-in defaults (config.py HelmValues.default)
+    PluginConfig default_config() const {
+        for (const auto& kv : configs) if (kv.first == "default") return kv.second;
+        if (configs.size() == 1) return configs[0].second;
+        return PluginConfig();
+    }
+};
+
+inline HelmValues parse_helm_values(const std::string& text) {
+    yaml::Node doc;
+    try { doc = yaml::parse(text); } catch (const yaml::Error& e) { throw Error(std::string("values.yaml is not valid YAML: ") + e.what()); }
+    if (doc.is_null()) doc.kind = yaml::Node::Map;
+    if (doc.kind != yaml::Node::Map) throw Error("values.yaml must be a mapping");
+    HelmValues v;
+    if (const yaml::Node* gfd = child_map(doc, "gfd", "gfd"))
+        if (const yaml::Node* en = gfd->get("enabled")) v.gfd_enabled = (en->kind == yaml::Node::Bool && en->b) || (en->kind == yaml::Node::Int && en->i) || (en->kind == yaml::Node::Str && !en->s.empty());
+    if (const yaml::Node* rc = doc.get("runtimeClassName")) if (rc->kind == yaml::Node::Str) v.runtime_class_name = rc->s;
+    if (const yaml::Node* cfg = child_map(doc, "config", "config"))
+        if (const yaml::Node* map = child_map(*cfg, "map", "config.map"))
+            for (const auto& kv : map->map) {
+                if (kv.second.kind != yaml::Node::Str) throw Error("config.map." + kv.first + " must be a YAML string (block scalar)");
+                v.raw_configs.emplace_back(kv.first, kv.second.s);
+                v.configs.emplace_back(kv.first, parse_plugin_config(kv.second.s));
+            }
+    return v;
+}
+
 // ---- replica annotation [RECALLED upstream AnnotatedID] -----------------------------------------
 inline std::string annotate(const std::string& uuid, int64_t replica) { return uuid + kReplicaSep + std::to_string(replica); }
 inline bool has_replica(const std::string& id) { return id.find(kReplicaSep) != std::string::npos; }

@@ -6,6 +6,7 @@
 //
 //   b200-device-plugin --config-file /config/config.yaml
 //   b200-device-plugin --check-config FILE          print the parsed configuration as JSON (parity tests)
+//   b200-device-plugin --check-values FILE          the same for the chart's values.yaml (gfd, runtimeClassName, config.map)
 //   b200-device-plugin --probe-once                 one active-probe round, labels on stdout
 #include <signal.h>
 
@@ -46,6 +47,42 @@ static int hpack_decode_stdin() {
     return 0;
 }
 
+static std::string config_json(const config::PluginConfig& c);
+
+// --check-values FILE: the Helm values file of the reference, parsed like config.py's parse_helm_values
+static int check_values(const std::string& path) {
+    std::ifstream f(path);
+    std::stringstream ss;
+    ss << f.rdbuf();
+    try {
+        const config::HelmValues v = config::parse_helm_values(ss.str());
+        std::string cfgs = "{", raws = "{";
+        for (size_t i = 0; i < v.configs.size(); ++i) {
+            cfgs += std::string(i ? "," : "") + json_str(v.configs[i].first) + ":" + config_json(v.configs[i].second);
+            raws += std::string(i ? "," : "") + json_str(v.raw_configs[i].first) + ":" + json_str(v.raw_configs[i].second);
+        }
+        printf("{\"ok\":true,\"gfd_enabled\":%s,\"runtime_class_name\":%s,\"configs\":%s},\"raw_configs\":%s},\"default\":%s}\n", v.gfd_enabled ? "true" : "false",
+               v.runtime_class_name.empty() ? "null" : json_str(v.runtime_class_name).c_str(), cfgs.c_str(), raws.c_str(), config_json(v.default_config()).c_str());
+    } catch (const config::Error& e) {
+        printf("{\"ok\":false,\"error\":%s}\n", json_str(e.what()).c_str());
+    }
+    return 0;
+}
+
+static std::string config_json(const config::PluginConfig& c) {
+    std::string res = "[";
+    for (size_t i = 0; i < c.time_slicing.resources.size(); ++i) {
+        const auto& r = c.time_slicing.resources[i];
+        res += std::string(i ? "," : "") + "{\"name\":" + json_str(r.name) + ",\"replicas\":" + std::to_string(r.replicas) +
+               ",\"rename\":" + (r.rename.empty() ? "null" : json_str(r.rename)) + "}";
+    }
+    res += "]";
+    return "{\"version\":" + json_str(c.version) + ",\"mig_strategy\":" + json_str(c.mig_strategy) + ",\"rename_by_default\":" +
+           (c.time_slicing.rename_by_default ? "true" : "false") + ",\"fail_requests_greater_than_one\":" +
+           (c.time_slicing.fail_requests_greater_than_one ? "true" : "false") + ",\"resources\":" + res + ",\"resource_name\":" + json_str(c.resource_name()) +
+           ",\"replicas\":" + std::to_string(c.replicas()) + ",\"is_shared\":" + (c.is_shared() ? "true" : "false") + "}";
+}
+
 static int check_config(const std::string& path) {
     std::ifstream f(path);
     std::stringstream ss;
@@ -84,6 +121,7 @@ int main(int argc, char** argv) {
         auto val = [&](std::string* out) { if (i + 1 >= argc) { fprintf(stderr, "%s needs a value\n", a.c_str()); exit(2); } *out = argv[++i]; };
         std::string v;
         if (a == "--check-config") { val(&v); return check_config(v); }
+        else if (a == "--check-values") { val(&v); return check_values(v); }
         else if (a == "--hpack-decode") return hpack_decode_stdin();
         else if (a == "--config-file") val(&config_file);
         else if (a == "--socket-dir") val(&socket_dir);

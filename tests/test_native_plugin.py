@@ -634,3 +634,29 @@ def test_limits_are_enforced_without_hurting_well_behaved_clients(stack):
     assert daemon.proc.poll() is None
     with kubelet.plugin_channel() as ch:
         assert len(next(api.DevicePluginStub(ch).ListAndWatch(api.Empty())).devices) == 8
+
+
+@pytest.mark.parametrize("variant", ["reference", "two-configs-keep", "no-gfd"])
+def test_values_yaml_parses_like_the_python_host(variant, tmp_path):
+    """/root/reference/values.yaml exactly as shipped (golden copy), plus variants of the chart values: gfd.enabled,
+    runtimeClassName and every config.map.<name> block scalar must come out as config.py reads them."""
+    text = G["reference_inputs"]["values.yaml"]["text"]
+    if variant == "two-configs-keep":
+        text = ("gfd:\n  enabled: false\nruntimeClassName: nvidia\nconfig:\n  map:\n    default: |\n      version: v1\n      flags:\n        migStrategy: none\n"
+                "    shared8: |-\n      version: v1\n      sharing:\n        timeSlicing:\n          renameByDefault: true\n          resources:\n"
+                "          - name: nvidia.com/gpu\n            replicas: 8\n")
+    elif variant == "no-gfd":
+        text = "runtimeClassName: nvidia   # nothing else\n"
+    path = tmp_path / "values.yaml"
+    path.write_text(text)
+    out = json.loads(subprocess.run([BIN, "--check-values", str(path)], capture_output=True, text=True, check=True).stdout)
+    want = cfgmod.parse_helm_values(text)
+    assert out["ok"] and out["gfd_enabled"] == want.gfd_enabled and out["runtime_class_name"] == want.runtime_class_name
+    assert out["raw_configs"] == want.raw_configs                     # block scalars byte for byte (|- strips, | keeps the newline)
+    assert list(out["configs"]) == list(want.configs)
+    for name, c in want.configs.items():
+        o = out["configs"][name]
+        assert (o["version"], o["mig_strategy"], o["rename_by_default"], o["resource_name"], o["replicas"], o["is_shared"]) == \
+            (c.version, c.mig_strategy, c.time_slicing.rename_by_default, c.resource_name(), c.replicas(), c.is_shared())
+    d = want.default
+    assert (out["default"]["resource_name"], out["default"]["replicas"]) == (d.resource_name(), d.replicas())
