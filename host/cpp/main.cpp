@@ -47,6 +47,63 @@ static int hpack_decode_stdin() {
     return 0;
 }
 
+// --labels-from-stdin: synthetic probe results in, rendered feature file out (CPU parity check of labels.hpp against
+// labels.py).  One record per line:
+//   hbm <gpu> <bytes> <mode 1|2|4> <gbs_median> <verified> <cache_resident>
+//   gemm <gpu> <tflops_median> <verified>
+//   passive <gpu> <links_total> <links_active> <fabric_state> <fabric_status> <fabric_health_mask>
+//   a2a <G> <verified> <min_pair_gbs> <G egress> <G ingress> <G*G pair, row-major>
+static int labels_from_stdin() {
+    std::map<int, std::vector<b200probe_hbm_result_t>> hbm;
+    std::map<int, b200probe_gemm_result_t> gemm;
+    std::map<int, b200probe_nvlink_status_t> passive;
+    bool have_a2a = false;
+    b200probe_a2a_result_t rep;
+    std::vector<double> pair;
+    memset(&rep, 0, sizeof(rep));
+    std::string line;
+    while (std::getline(std::cin, line)) {
+        std::istringstream in(line);
+        std::string kind;
+        in >> kind;
+        if (kind == "hbm") {
+            int gpu; b200probe_hbm_result_t r;
+            memset(&r, 0, sizeof(r));
+            unsigned long long bytes;
+            in >> gpu >> bytes >> r.mode >> r.gbs_median >> r.verified >> r.cache_resident;
+            r.bytes = bytes;
+            hbm[gpu].push_back(r);
+        } else if (kind == "gemm") {
+            int gpu; b200probe_gemm_result_t r;
+            memset(&r, 0, sizeof(r));
+            in >> gpu >> r.tflops_median >> r.verified;
+            gemm[gpu] = r;
+        } else if (kind == "passive") {
+            int gpu; b200probe_nvlink_status_t st;
+            memset(&st, 0, sizeof(st));
+            in >> gpu >> st.links_total >> st.links_active >> st.fabric_state >> st.fabric_status >> st.fabric_health_mask;
+            passive[gpu] = st;
+        } else if (kind == "a2a") {
+            in >> rep.g >> rep.verified >> rep.min_pair_gbs;
+            for (int i = 0; i < rep.g; ++i) in >> rep.egress_gbs[i];
+            for (int i = 0; i < rep.g; ++i) in >> rep.ingress_gbs[i];
+            pair.assign((size_t)(rep.g * rep.g), 0.0);
+            for (auto& v : pair) in >> v;
+            have_a2a = true;
+        }
+    }
+    labels::Thresholds th;
+    labels::Labels l;
+    auto merge = [&](const labels::Labels& got) { for (const auto& kv : got) l[kv.first] = kv.second; };
+    if (!hbm.empty()) merge(labels::hbm_labels(hbm, th));
+    if (!gemm.empty()) merge(labels::gemm_labels(gemm, th));
+    merge(labels::nvlink_passive_labels(passive));
+    if (have_a2a) merge(labels::nvlink_labels(rep, pair, th));
+    labels::gate_label(&l);
+    fputs(labels::render(l).c_str(), stdout);
+    return 0;
+}
+
 static std::string config_json(const config::PluginConfig& c);
 
 // --check-values FILE: the Helm values file of the reference, parsed like config.py's parse_helm_values
@@ -122,6 +179,7 @@ int main(int argc, char** argv) {
         std::string v;
         if (a == "--check-config") { val(&v); return check_config(v); }
         else if (a == "--check-values") { val(&v); return check_values(v); }
+        else if (a == "--labels-from-stdin") return labels_from_stdin();
         else if (a == "--hpack-decode") return hpack_decode_stdin();
         else if (a == "--config-file") val(&config_file);
         else if (a == "--socket-dir") val(&socket_dir);

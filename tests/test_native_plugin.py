@@ -660,3 +660,57 @@ def test_values_yaml_parses_like_the_python_host(variant, tmp_path):
             (c.version, c.mig_strategy, c.time_slicing.rename_by_default, c.resource_name(), c.replicas(), c.is_shared())
     d = want.default
     assert (out["default"]["resource_name"], out["default"]["replicas"]) == (d.resource_name(), d.replicas())
+
+
+def test_label_rules_match_the_python_host_on_synthetic_probe_results():
+    """labels.hpp against labels.py on random probe outcomes: same keys, same rounding (half-to-even), same
+    verdict sizes, same thresholds, same gate — compared as rendered feature files."""
+    import random
+    from types import SimpleNamespace as NS
+
+    from k3s_nvidia_b200 import labels as L
+
+    rng = random.Random(4242)
+    mode_name = {1: "read", 2: "write", 4: "copy"}
+    for trial in range(60):
+        lines, hbm, gemm, passive = [], {}, {}, {}
+        ngpu = rng.randint(1, 8)
+        for gpu in range(ngpu):
+            if rng.random() < 0.9:
+                pts = []
+                for lg in rng.sample(range(20, 31), rng.randint(1, 6)):
+                    for mode in rng.sample([1, 2, 4], rng.randint(1, 3)):
+                        gbs = rng.choice([rng.uniform(5000, 7300), rng.uniform(100, 6000), float(rng.randint(5000, 7000)) + 0.5])
+                        ver = rng.choice([1, 1, 1, 0, -1])
+                        resident = int((2 if mode == 4 else 1) * (1 << lg) <= 126 << 20)
+                        lines.append(f"hbm {gpu} {1 << lg} {mode} {gbs!r} {ver} {resident}")
+                        pts.append(NS(bytes=1 << lg, mode=mode_name[mode], gbs_median=gbs, verified=ver, cache_resident=bool(resident)))
+                hbm[gpu] = pts
+            if rng.random() < 0.8:
+                tf, ver = rng.choice([rng.uniform(900, 1700), 1169.14, 1250.5]), rng.choice([1, 1, 0])
+                lines.append(f"gemm {gpu} {tf!r} {ver}")
+                gemm[gpu] = NS(tflops_median=tf, verified=ver)
+            if rng.random() < 0.8:
+                total = rng.choice([18, 18, 0, 12])
+                st = dict(links_total=total, links_active=rng.choice([total, total, max(0, total - 2)]), fabric_state=rng.choice([3, 3, -1, 2]),
+                          fabric_status=rng.choice([0, 0, 9]), fabric_health_mask=rng.choice([0, 0, 1, 2, 0x10]))
+                lines.append(f"passive {gpu} {st['links_total']} {st['links_active']} {st['fabric_state']} {st['fabric_status']} {st['fabric_health_mask']}")
+                passive[gpu] = st
+        want = {}
+        th = L.Thresholds()
+        if hbm:
+            want.update(L.hbm_labels(hbm, th))
+        if gemm:
+            want.update(L.gemm_labels(gemm, th))
+        want.update(L.nvlink_passive_labels(passive))
+        if ngpu >= 2 and rng.random() < 0.8:
+            g = ngpu
+            egress = [rng.choice([rng.uniform(600, 710), 671.5, 672.0]) for _ in range(g)]
+            ingress = [rng.uniform(600, 710) for _ in range(g)]
+            pair = [[0.0 if i == j else rng.choice([rng.uniform(80, 110), 0.0]) for j in range(g)] for i in range(g)]
+            ver, mn = rng.choice([1, 1, 0]), rng.uniform(80, 100)
+            lines.append(f"a2a {g} {ver} {mn!r} " + " ".join(repr(x) for x in egress + ingress + [v for row in pair for v in row]))
+            want.update(L.nvlink_labels(NS(g=g, verified=ver, egress_gbs=egress, ingress_gbs=ingress, pair_gbs=pair, min_pair_gbs=mn), th))
+        want.update(L.gate_label(want))
+        out = subprocess.run([BIN, "--labels-from-stdin"], input="\n".join(lines) + "\n", capture_output=True, text=True, check=True).stdout
+        assert out == L.render(want), (trial, lines)
