@@ -17,8 +17,8 @@
 #include "labels.hpp"
 #include "plugin.hpp"
 
-static std::atomic<bool> g_stop{false};
-static void on_signal(int) { g_stop = true; }
+static std::atomic<bool> g_stop{false}, g_reload{false};
+static void on_signal(int sig) { if (sig == SIGHUP) g_reload = true; else g_stop = true; }
 
 static std::string json_str(const std::string& s) {
     std::string o = "\"";
@@ -219,15 +219,37 @@ int main(int argc, char** argv) {
     sigaction(SIGTERM, &sa, nullptr);
     sigaction(SIGINT, &sa, nullptr);
     signal(SIGPIPE, SIG_IGN);
+    sigaction(SIGHUP, &sa, nullptr);
     try {
-        plugin::DevicePlugin dp(cfg, socket_dir, kubelet_socket, health_timeout_ms);
-        dp.start(watch_period, health);
+        std::unique_ptr<plugin::DevicePlugin> dp(new plugin::DevicePlugin(cfg, socket_dir, kubelet_socket, health_timeout_ms));
+        dp->start(watch_period, health);
         std::unique_ptr<labels::ActiveProbeRunner> runner;
         if (active) { runner.reset(new labels::ActiveProbeRunner(features_dir, probe_interval)); runner->start(); }
-        plugin::logf("serving '%s' on %s (%zu devices)", dp.resource().c_str(), dp.socket_path().c_str(), dp.devices().size());
-        while (!g_stop) usleep(100000);
+        plugin::logf("serving '%s' on %s (%zu devices)", dp->resource().c_str(), dp->socket_path().c_str(), dp->devices().size());
+        while (!g_stop) {
+            usleep(100000);
+            if (!g_reload.exchange(false)) continue;
+            // SIGHUP: the chart's config-manager sidecar rewrote the config file [RECALLED]; take the new document if it
+            // parses (a bad one keeps the running configuration), re-enumerate, serve again and re-Register.
+            try {
+                std::ifstream f(config_file);
+                if (!f) throw config::Error("cannot open " + config_file);
+                std::stringstream ss;
+                ss << f.rdbuf();
+                const config::PluginConfig fresh = config::parse_plugin_config(ss.str());
+                dp->stop();
+                dp.reset();
+                b200probe_health_close();
+                dp.reset(new plugin::DevicePlugin(fresh, socket_dir, kubelet_socket, health_timeout_ms));
+                dp->start(watch_period, health);
+                plugin::logf("reloaded %s: serving '%s' on %s (%zu devices)", config_file.c_str(), dp->resource().c_str(), dp->socket_path().c_str(),
+                             dp->devices().size());
+            } catch (const config::Error& e) {
+                plugin::logf("reload of %s rejected, keeping the running configuration: %s", config_file.c_str(), e.what());
+            }
+        }
         if (runner) runner->stop();
-        dp.stop();
+        if (dp) dp->stop();
     } catch (const std::exception& e) { plugin::logf("fatal: %s", e.what()); b200probe_shutdown(); return 1; }
     b200probe_shutdown();
     return 0;

@@ -322,6 +322,8 @@ def main(argv=None) -> int:
     logging.basicConfig(level=logging.INFO, format="%(asctime)s %(name)s %(message)s")
     with open(args.config_file) as f:
         cfg = parse_plugin_config(f.read())
+    import signal
+
     probe = Probe()
     plugin = DevicePlugin(probe, cfg, socket_dir=args.socket_dir)
     plugin.start()
@@ -329,9 +331,24 @@ def main(argv=None) -> int:
     if not args.no_active_probe:
         runner = ActiveProbeRunner(probe, features_dir=args.features_dir, interval_s=args.probe_interval)
         runner.start()
+    reload_requested = threading.Event()
+    signal.signal(signal.SIGHUP, lambda *_: reload_requested.set())
     try:
         while True:
-            time.sleep(3600)
+            if not reload_requested.wait(1.0):
+                continue
+            reload_requested.clear()
+            # SIGHUP: the chart's config-manager sidecar rewrote the config file [RECALLED] (same rule as host/cpp/main.cpp)
+            try:
+                with open(args.config_file) as f:
+                    fresh = parse_plugin_config(f.read())
+            except (OSError, ValueError) as e:
+                log.error("reload of %s rejected, keeping the running configuration: %s", args.config_file, e)
+                continue
+            plugin.stop()
+            plugin = DevicePlugin(probe, fresh, socket_dir=args.socket_dir)
+            plugin.start()
+            log.info("reloaded %s: serving '%s' (%d devices)", args.config_file, plugin.resource, len(plugin.devices))
     except KeyboardInterrupt:
         pass
     finally:

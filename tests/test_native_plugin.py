@@ -714,3 +714,32 @@ def test_label_rules_match_the_python_host_on_synthetic_probe_results():
         want.update(L.gate_label(want))
         out = subprocess.run([BIN, "--labels-from-stdin"], input="\n".join(lines) + "\n", capture_output=True, text=True, check=True).stdout
         assert out == L.render(want), (trial, lines)
+
+
+def test_sighup_reloads_the_config_document(stack):
+    """a rewritten config file + SIGHUP (what the chart's config-manager does [RECALLED]) -> new
+    replica count advertised after a fresh Register; a document that does not parse keeps the running one."""
+    kubelet, daemon = stack
+    cfg = os.path.join(daemon.dir, "config.yaml")
+    n0 = len(kubelet.requests)
+    open(cfg, "w").write("version: v1\nsharing:\n  timeSlicing:\n    renameByDefault: true\n    resources:\n    - name: nvidia.com/gpu\n      replicas: 2\n")
+    kubelet.event.clear()
+    daemon.proc.send_signal(signal.SIGHUP)
+    assert kubelet.event.wait(10), daemon.logtext()
+    t_end = time.time() + 5
+    while "reloaded" not in daemon.logtext() and time.time() < t_end:
+        time.sleep(0.02)
+    r = kubelet.requests[-1]
+    assert len(kubelet.requests) == n0 + 1 and (r.resource_name, r.endpoint) == ("nvidia.com/gpu.shared", "nvidia-gpu-shared.sock")
+    with kubelet.plugin_channel() as ch:
+        first = next(api.DevicePluginStub(ch).ListAndWatch(api.Empty()))
+        assert [d.ID for d in first.devices] == [f"{U0}::0", f"{U0}::1", f"{U1}::0", f"{U1}::1"]
+    open(cfg, "w").write("version: v7\n")
+    daemon.proc.send_signal(signal.SIGHUP)
+    t_end = time.time() + 5
+    while "rejected" not in daemon.logtext() and time.time() < t_end:
+        time.sleep(0.02)
+    assert "rejected, keeping the running configuration: unknown version: 'v7'" in daemon.logtext()
+    assert len(kubelet.requests) == n0 + 1 and daemon.proc.poll() is None
+    with kubelet.plugin_channel() as ch:
+        assert len(next(api.DevicePluginStub(ch).ListAndWatch(api.Empty())).devices) == 4
