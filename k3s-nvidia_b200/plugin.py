@@ -318,21 +318,37 @@ def main(argv=None) -> int:
     ap.add_argument("--features-dir", default="/etc/kubernetes/node-feature-discovery/features.d")
     ap.add_argument("--probe-interval", type=float, default=float(os.environ.get("B200PROBE_INTERVAL_S", "600")))
     ap.add_argument("--no-active-probe", action="store_true")
+    ap.add_argument("--kubelet-socket", default=None)
+    ap.add_argument("--nvml-path", default=None)
+    ap.add_argument("--watch-period", type=float, default=1.0)
+    ap.add_argument("--health-timeout-ms", type=int, default=5000)
+    ap.add_argument("--no-health", action="store_true")
     args = ap.parse_args(argv)
     logging.basicConfig(level=logging.INFO, format="%(asctime)s %(name)s %(message)s")
     with open(args.config_file) as f:
         cfg = parse_plugin_config(f.read())
     import signal
 
-    probe = Probe()
-    plugin = DevicePlugin(probe, cfg, socket_dir=args.socket_dir)
-    plugin.start()
+    probe = Probe(args.nvml_path)
+
+    def make(c):
+        dp = DevicePlugin(probe, c, socket_dir=args.socket_dir, kubelet_socket=args.kubelet_socket, health_timeout_ms=args.health_timeout_ms)
+        dp.start(watch_kubelet_period=args.watch_period, health=not args.no_health)
+        return dp
+
+    plugin = make(cfg)
+    log.info("serving '%s' on %s (%d devices)", plugin.resource, plugin.socket_path, len(plugin.devices))
     runner = None
     if not args.no_active_probe:
         runner = ActiveProbeRunner(probe, features_dir=args.features_dir, interval_s=args.probe_interval)
         runner.start()
     reload_requested = threading.Event()
     signal.signal(signal.SIGHUP, lambda *_: reload_requested.set())
+
+    def _term(*_):
+        raise KeyboardInterrupt
+
+    signal.signal(signal.SIGTERM, _term)
     try:
         while True:
             if not reload_requested.wait(1.0):
@@ -346,8 +362,7 @@ def main(argv=None) -> int:
                 log.error("reload of %s rejected, keeping the running configuration: %s", args.config_file, e)
                 continue
             plugin.stop()
-            plugin = DevicePlugin(probe, fresh, socket_dir=args.socket_dir)
-            plugin.start()
+            plugin = make(fresh)
             log.info("reloaded %s: serving '%s' (%d devices)", args.config_file, plugin.resource, len(plugin.devices))
     except KeyboardInterrupt:
         pass

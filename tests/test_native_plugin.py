@@ -30,6 +30,8 @@ def _binary():
 
 
 class Daemon:
+    CMD = None          # None = the native binary; PyDaemon runs the Python twin with the same flags
+
     def __init__(self, d, config_text, extra_env=None, args=()):
         self.dir = d
         self.events = os.path.join(d, "events.txt")
@@ -40,7 +42,7 @@ class Daemon:
         env = dict(os.environ, MOCK_NVML_DEVICES="2", MOCK_NVML_EVENT_FILE=self.events)
         env.update(extra_env or {})
         self.log = open(os.path.join(d, "daemon.log"), "w")
-        self.proc = subprocess.Popen([BIN, "--config-file", cfg, "--socket-dir", d, "--nvml-path", _oracle.MOCK_NVML, "--no-active-probe",
+        self.proc = subprocess.Popen([*(self.CMD or [BIN]), "--config-file", cfg, "--socket-dir", d, "--nvml-path", _oracle.MOCK_NVML, "--no-active-probe",
                                       "--watch-period", "0.05", "--health-timeout-ms", "5", *args], env=env, stderr=self.log)
 
     def wait_serving(self, timeout=10.0):
@@ -72,6 +74,27 @@ class Daemon:
 
     def logtext(self):
         return open(os.path.join(self.dir, "daemon.log")).read()
+
+
+class PyDaemon(Daemon):
+    import sys as _sys
+    CMD = [_sys.executable, "-m", "k3s_nvidia_b200.plugin"]
+
+
+@pytest.fixture(params=["native", "python"])
+def both_hosts(request, tmp_path, monkeypatch):
+    """The same CLI contract for both hosts: flags, log lines the tests key on, signals."""
+    monkeypatch.setenv("PYTHONPATH", ROOT + os.pathsep + os.environ.get("PYTHONPATH", ""))
+    d = str(tmp_path)
+    kubelet = FakeKubelet(d)
+    kubelet.start()
+    daemon = (Daemon if request.param == "native" else PyDaemon)(d, VALUES.raw_configs["default"])
+    try:
+        assert kubelet.event.wait(30) and daemon.wait_serving(30), "host did not register: " + daemon.logtext()
+        yield kubelet, daemon
+    finally:
+        daemon.stop()
+        kubelet.stop()
 
 
 @pytest.fixture
@@ -716,10 +739,11 @@ def test_label_rules_match_the_python_host_on_synthetic_probe_results():
         assert out == L.render(want), (trial, lines)
 
 
-def test_sighup_reloads_the_config_document(stack):
+def test_sighup_reloads_the_config_document(both_hosts):
     """a rewritten config file + SIGHUP (what the chart's config-manager does [RECALLED]) -> new
-    replica count advertised after a fresh Register; a document that does not parse keeps the running one."""
-    kubelet, daemon = stack
+    replica count advertised after a fresh Register; a document that does not parse keeps the running one.
+    Run against the native daemon and the Python twin started from its CLI."""
+    kubelet, daemon = both_hosts
     cfg = os.path.join(daemon.dir, "config.yaml")
     n0 = len(kubelet.requests)
     open(cfg, "w").write("version: v1\nsharing:\n  timeSlicing:\n    renameByDefault: true\n    resources:\n    - name: nvidia.com/gpu\n      replicas: 2\n")
@@ -740,6 +764,14 @@ def test_sighup_reloads_the_config_document(stack):
     while "rejected" not in daemon.logtext() and time.time() < t_end:
         time.sleep(0.02)
     assert "rejected, keeping the running configuration: unknown version: 'v7'" in daemon.logtext()
+    daemon.push(0, 0, 79)                        # the reloaded instance still follows the passive health events
+    with kubelet.plugin_channel() as ch:
+        stream = api.DevicePluginStub(ch).ListAndWatch(api.Empty())
+        seen = next(stream)
+        if all(d.health == "Healthy" for d in seen.devices):
+            seen = next(stream)
+        assert [d.health for d in seen.devices] == ["Unhealthy", "Unhealthy", "Healthy", "Healthy"]
+        stream.cancel()
     assert len(kubelet.requests) == n0 + 1 and daemon.proc.poll() is None
     with kubelet.plugin_channel() as ch:
         assert len(next(api.DevicePluginStub(ch).ListAndWatch(api.Empty())).devices) == 4
