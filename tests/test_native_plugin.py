@@ -775,3 +775,55 @@ def test_sighup_reloads_the_config_document(both_hosts):
     assert len(kubelet.requests) == n0 + 1 and daemon.proc.poll() is None
     with kubelet.plugin_channel() as ch:
         assert len(next(api.DevicePluginStub(ch).ListAndWatch(api.Empty())).devices) == 4
+
+
+def test_random_frame_sequences_never_crash_the_transport(stack):
+    """Structure-aware fuzz of the HTTP/2 layer: valid preface, then random frames (all types, random flags, stream
+    ids, lengths, HPACK-ish payloads).  Whatever the answer (GOAWAY, RST, silence), the daemon survives and serves."""
+    import random
+    import socket
+    import struct
+
+    kubelet, daemon = stack
+    path = os.path.join(daemon.dir, "nvidia-gpu.sock")
+    rng = random.Random(9113)
+
+    def frame(t, flags, stream, payload=b""):
+        return struct.pack(">I", len(payload))[1:] + bytes([t, flags]) + struct.pack(">I", stream & 0x7FFFFFFF) + payload
+
+    good_hdr = b"\x83\x86\x44\x1e/v1beta1.DevicePlugin/Allocate" + b"\x41\x09localhost" + b"\x5f\x10application/grpc" + b"\x40\x02te\x08trailers"
+    for _ in range(150):
+        data = b"PRI * HTTP/2.0\r\n\r\nSM\r\n\r\n" + (frame(4, 0, 0) if rng.random() < 0.8 else b"")
+        for _ in range(rng.randint(1, 12)):
+            t = rng.choice([0, 0, 1, 1, 1, 2, 3, 4, 5, 6, 7, 8, 9, 9, 0x42])
+            flags = rng.choice([0, 1, 4, 5, 8, 0x20, 0x24, 0x2D, rng.randrange(256)])
+            stream = rng.choice([0, 1, 1, 3, 5, 2, rng.randrange(1 << 31)])
+            kind = rng.random()
+            if kind < 0.3:
+                payload = good_hdr
+            elif kind < 0.5:
+                payload = b"\x00" + struct.pack(">I", rng.choice([0, 2, 5, 1 << 20])) + os.urandom(rng.randint(0, 40))     # gRPC-framed-ish DATA
+            elif kind < 0.7:
+                payload = os.urandom(rng.choice([0, 1, 4, 5, 6, 8, 9, 64, 300]))
+            else:
+                payload = bytes(rng.choice([0x80, 0xFF, 0x40, 0x20, 0x3F, 0x00, 0x7F, 0x0F]) for _ in range(rng.randint(0, 24)))
+            data += frame(t, flags, stream, payload)
+        s = socket.socket(socket.AF_UNIX, socket.SOCK_STREAM)
+        s.settimeout(0.05)
+        try:
+            s.connect(path)
+            s.sendall(data)
+            try:
+                s.recv(65536)
+            except (socket.timeout, ConnectionError):
+                pass
+        except (BrokenPipeError, ConnectionError):
+            pass
+        finally:
+            s.close()
+    assert daemon.proc.poll() is None, daemon.logtext()
+    with kubelet.plugin_channel() as ch:
+        stub = api.DevicePluginStub(ch)
+        assert len(next(stub.ListAndWatch(api.Empty())).devices) == 8
+        r = stub.Allocate(api.AllocateRequest(container_requests=[api.ContainerAllocateRequest(devices_ids=[f"{U0}::0"])]))
+        assert dict(r.container_responses[0].envs) == {"NVIDIA_VISIBLE_DEVICES": U0}
