@@ -240,7 +240,10 @@ typedef struct b200probe_a2a_result {
 } b200probe_a2a_result_t;
 
 /* Single process, all GPUs (how the plugin daemon runs).  cuda_ordinals[g]; pair_gbs is g*g
- * row-major [src][dst], diagonal 0. */
+ * row-major [src][dst], diagonal 0.  PEER_PAIR: each pair measured alone.  PEER_ALL: under PUSH_SYNC
+ * the exchange moves one pair per step (src -> (src+t) mod g) and the kernel time-stamps the steps, so
+ * the entry is that pair's own rate inside the full exchange; for the free-running schedules it is the
+ * pair's share egress/(g-1). */
 int b200probe_nvlink_a2a(const int* cuda_ordinals, int g, const b200probe_a2a_cfg_t* cfg,
                          double* pair_gbs, b200probe_a2a_result_t* out);
 

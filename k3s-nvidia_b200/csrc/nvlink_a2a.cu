@@ -33,6 +33,7 @@
 #include <pthread.h>
 
 #include <algorithm>
+#include <cstddef>
 #include <vector>
 
 #include "common.h"
@@ -72,6 +73,14 @@ struct SyncPage {
     uint32_t flag[kMaxWorld];
     uint32_t cnt;
     uint32_t epoch;
+    // PUSH_SYNC, barrier before every step: this device's %globaltimer when it left barrier b (= start of step b+1),
+    // and in slot world-1 when CTA 0 had drained its last store.  Step t moves exactly one pair, rank -> (rank+t) mod G,
+    // so consecutive differences are per-pair transfer times measured under the full exchange.
+    unsigned long long step_ns[kMaxWorld + 1];
+    // the same clock when the LAST CTA of the grid had drained its stores (CTA 0 alone finishes a little early, which
+    // made the last step of every rank look 5-50 % faster than the others: profiles/a2a_pair_matrix_r01_g4.txt)
+    unsigned int done_cnt;
+    unsigned long long end_ns;
 };
 static_assert(sizeof(SyncPage) <= B200PROBE_A2A_SYNC_BYTES, "sync page");
 
@@ -241,6 +250,11 @@ __global__ void __launch_bounds__(kRingWarps * 32) a2a_stagger_kernel(XArgs a) {
                         __nanosleep(200);
                     }
                 }
+                if (blockIdx.x == 0 && lane == 0 && a.sync_every == 1) {
+                    unsigned long long now_ns;
+                    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now_ns));
+                    mine->step_ns[b] = now_ns;
+                }
             }
             __syncthreads();
         }
@@ -268,6 +282,18 @@ __global__ void __launch_bounds__(kRingWarps * 32) a2a_stagger_kernel(XArgs a) {
         }
     }
     if (lane == 0) bulk_wait_all();
+    if (sync && a.sync_every == 1) {
+        __syncthreads();                                   // every warp of this CTA has drained its stores
+        if (threadIdx.x == 0) {
+            unsigned long long now_ns;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now_ns));
+            if (blockIdx.x == 0) mine->step_ns[a.world - 1] = now_ns;
+            if (atomicAdd(&mine->done_cnt, 1u) == gridDim.x - 1) {          // last CTA of the grid: the exchange is over
+                mine->end_ns = now_ns;
+                atomicExch(&mine->done_cnt, 0u);
+            }
+        }
+    }
 }
 
 // ---- start gate (single-process probe): every device's exchange kernel is queued behind one of these and
@@ -693,6 +719,22 @@ int b200probe_nvlink_a2a(const int* ordinals, int g, const b200probe_a2a_cfg_t* 
         out->ms_best = *std::min_element(wall.begin(), wall.end());
         const double payload = (double)(g - 1) * (double)S;
         double mn = 1e300, mx = 0;
+        // PUSH_SYNC with a barrier before every step: the kernel stamped each step, and a step moves one pair alone
+        // (rank -> (rank+t) mod G), so the matrix holds real per-pair rates of the last exchange instead of shares.
+        std::vector<std::vector<unsigned long long>> stamps;
+        if (cfg.variant == B200PROBE_A2A_PUSH_SYNC && !getenv("B200PROBE_A2A_SYNC_EVERY")) {
+            stamps.assign(g, std::vector<unsigned long long>(kMaxWorld + 1, 0));
+            for (int i = 0; i < g; ++i) {
+                B200_CUDA_TRY(cudaSetDevice(ctx.d[i].ordinal));
+                SyncPage page;
+                B200_CUDA_TRY(cudaMemcpy(&page, ctx.d[i].window + 2ull * g * S, sizeof(page), cudaMemcpyDeviceToHost));
+                for (int t = 0; t <= kMaxWorld; ++t) stamps[i][t] = page.step_ns[t];
+                if (page.end_ns > stamps[i][g - 1]) stamps[i][g - 1] = page.end_ns;      // end of the last step = the last CTA's drain, not CTA 0's
+                bool ordered = true;
+                for (int t = 1; t < g; ++t) ordered = ordered && stamps[i][t] > stamps[i][t - 1];
+                if (!ordered) { stamps.clear(); break; }                                 // a launch that lost the barrier: fall back to shares
+            }
+        }
         for (int i = 0; i < g; ++i) {
             const double own = payload / (median_of(per_dev[i]) * 1e-3) / 1e9;      // the direction rank i's kernel drives
             const double common = payload / (out->ms_median * 1e-3) / 1e9;          // the other direction, over the common window
@@ -700,7 +742,11 @@ int b200probe_nvlink_a2a(const int* ordinals, int g, const b200probe_a2a_cfg_t* 
             out->ingress_gbs[i] = mix ? own : pull ? own : common;
             for (int j = 0; j < g; ++j) {
                 if (i == j) continue;
-                const double gbs = own / (g - 1);                                   // per-pair share under full concurrency
+                double gbs = own / (g - 1);                                         // per-pair share under full concurrency
+                if (!stamps.empty()) {
+                    const int t = (j - i + g) % g;                                  // pair i -> j is step t of rank i
+                    gbs = (double)S / (double)(stamps[i][t] - stamps[i][t - 1]);      // bytes per ns = GB/s
+                }
                 if (pair_gbs) pair_gbs[pull ? j * g + i : i * g + j] = gbs;
                 mn = std::min(mn, gbs); mx = std::max(mx, gbs);
             }

@@ -58,7 +58,7 @@ def test_exchange_lands_oracle_pattern_in_every_recv_slot(env, S, variant):
     for dst in range(g):
         host = wins[dst].cpu().numpy()
         assert (host[2 * g * S + SYNC:] == 0x5A).all(), "wrote past the window"
-        assert not host[2 * g * S + 72:2 * g * S + SYNC].any(), "sync page: only flag[16], cnt, epoch may change"
+        assert not host[2 * g * S + 72 + 8 * 17 + 16:2 * g * S + SYNC].any(), "sync page: only flag[16], cnt, epoch, step_ns[17], done_cnt, end_ns may change"
         for src in range(g):
             want = _oracle.pattern(o, 0, S // 4, o.oracle_a2a_chunk_seed(SEED, src, dst))
             got = host[src * S:(src + 1) * S].view(np.uint32)
@@ -110,6 +110,14 @@ def test_single_process_probe_verifies_and_reports(env, mode, variant):
             assert (rep.pair_gbs[i][j] > 0) == (i != j)
     if mode != 1:
         assert all(x > 0 for x in rep.egress_gbs) and all(x > 0 for x in rep.ingress_gbs) and rep.ms_median > 0
+    if mode == 0 and variant == 7 and g > 1:
+        # PUSH_SYNC stamps its steps: each pair's rate is its own (one pair per step), not the egress share,
+        # and the steps of one rank add up to its exchange
+        for i in range(g):
+            row = [rep.pair_gbs[i][j] for j in range(g) if j != i]
+            assert min(row) > 1.5 * rep.egress_gbs[i] / max(g - 1, 2) or g == 2
+            total_ms = sum((8 << 20) / (x * 1e6) for x in row)
+            assert 0.5 * rep.ms_median < total_ms < 1.5 * rep.ms_median
 
 
 def test_full_size_exchange_properties(env):
