@@ -122,16 +122,40 @@ def cpu_copy_sample(o, threads: int, sample_bytes: int, target_s: float):
 
 
 def nvml_poll_timing(o):
-    """The reference's real path (passive NVML enumerate + XID event wait), timed on this host."""
+    """The reference's real path (passive NVML enumerate + XID event wait), timed on this host the way SURVEY.md
+    §8d config 1 asks: 1000 iterations after 10 warm-ups, single thread; the C twin and, where importable, pynvml."""
+    out = None
     try:
         if o.oracle_ph_open(None, None) != 0:
             return None
-        enum_us = o.oracle_ph_time_enumerate(200)
-        poll_us = o.oracle_ph_time_poll(200, 0)
+        o.oracle_ph_time_enumerate(10)
+        o.oracle_ph_time_poll(10, 0)
+        enum_us = o.oracle_ph_time_enumerate(1000)
+        poll_us = o.oracle_ph_time_poll(1000, 0)
         o.oracle_ph_close()
-        return {"enumerate_us": round(enum_us, 2), "poll_us": round(poll_us, 2), "iters": 200, "threads": 1}
+        out = {"enumerate_us": round(enum_us, 2), "poll_us": round(poll_us, 2), "iters": 1000, "warmup": 10, "threads": 1}
     except Exception:  # noqa: BLE001
         return None
+    try:
+        import pynvml as nv
+
+        nv.nvmlInit()
+
+        def enumerate_once():
+            for i in range(nv.nvmlDeviceGetCount()):
+                h = nv.nvmlDeviceGetHandleByIndex(i)
+                nv.nvmlDeviceGetUUID(h), nv.nvmlDeviceGetName(h), nv.nvmlDeviceGetMemoryInfo(h), nv.nvmlDeviceGetCudaComputeCapability(h)
+
+        for _ in range(10):
+            enumerate_once()
+        t0 = time.perf_counter()
+        for _ in range(1000):
+            enumerate_once()
+        out["pynvml_enumerate_us"] = round((time.perf_counter() - t0) * 1e3, 2)      # microseconds per enumerate (1000 iterations)
+        nv.nvmlShutdown()
+    except Exception:  # noqa: BLE001
+        pass
+    return out
 
 
 def run_reference(args):
