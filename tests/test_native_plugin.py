@@ -827,3 +827,43 @@ def test_random_frame_sequences_never_crash_the_transport(stack):
         assert len(next(stub.ListAndWatch(api.Empty())).devices) == 8
         r = stub.Allocate(api.AllocateRequest(container_requests=[api.ContainerAllocateRequest(devices_ids=[f"{U0}::0"])]))
         assert dict(r.container_responses[0].envs) == {"NVIDIA_VISIBLE_DEVICES": U0}
+
+
+def test_committed_huffman_table_is_what_libnghttp2_implements(tmp_path):
+    """host/cpp/hpack_huffman.inc regenerated from the system libnghttp2 (tools/gen_hpack_huffman.py) is byte-identical
+    to the committed file: the table is pinned to an independent implementation of RFC 7541 Appendix B."""
+    import ctypes.util
+    import sys
+
+    if not ctypes.util.find_library("nghttp2"):
+        pytest.skip("libnghttp2 not on this box")
+    out = tmp_path / "huff.inc"
+    subprocess.run([sys.executable, os.path.join(ROOT, "tools", "gen_hpack_huffman.py"), str(out)], check=True, capture_output=True, timeout=300)
+    assert out.read_text() == open(os.path.join(ROOT, "host", "cpp", "hpack_huffman.inc")).read()
+
+
+def test_unshared_config_and_index_strategy(tmp_path):
+    """No time-slicing: bare UUIDs are advertised and preferred allocation is required-first; deviceIDStrategy
+    index makes Allocate answer with NVML indices (both as plugin.py does)."""
+    d = str(tmp_path)
+    kubelet = FakeKubelet(d)
+    kubelet.start()
+    daemon = Daemon(d, "version: v1\nflags:\n  migStrategy: none\n  plugin:\n    deviceIDStrategy: index\n", extra_env={"MOCK_NVML_DEVICES": "4"})
+    try:
+        assert kubelet.event.wait(10) and daemon.wait_serving(), daemon.logtext()
+        with kubelet.plugin_channel() as ch:
+            stub = api.DevicePluginStub(ch)
+            ids = [x.ID for x in next(stub.ListAndWatch(api.Empty())).devices]
+            assert ids == [f"GPU-b2000000-0000-4000-8000-00000000000{i}" for i in range(4)]
+            resp = stub.Allocate(api.AllocateRequest(container_requests=[api.ContainerAllocateRequest(devices_ids=[ids[2], ids[0]])]))
+            assert dict(resp.container_responses[0].envs) == {"NVIDIA_VISIBLE_DEVICES": "2,0"}
+            pref = stub.GetPreferredAllocation(api.PreferredAllocationRequest(container_requests=[
+                api.ContainerPreferredAllocationRequest(available_deviceIDs=ids, must_include_deviceIDs=[ids[3]], allocation_size=2)]))
+            assert list(pref.container_responses[0].deviceIDs) == [ids[3], ids[0]]
+            with pytest.raises(grpc.RpcError) as e:
+                stub.GetPreferredAllocation(api.PreferredAllocationRequest(container_requests=[
+                    api.ContainerPreferredAllocationRequest(available_deviceIDs=ids[:1], allocation_size=2)]))
+            assert "not enough available devices" in e.value.details()
+    finally:
+        daemon.stop()
+        kubelet.stop()
