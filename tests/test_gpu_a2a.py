@@ -80,8 +80,8 @@ def test_only_peer_selectors(env):
     st0 = torch.cuda.current_stream(0).cuda_stream
     p._check(p.lib.b200probe_a2a_exchange(0, 0, g, peers, S, SEED, 0, 0, -2, st0), "exchange -2")     # peers only
     torch.cuda.synchronize(0)
-    # AUTO + all peers = PUSH_SYNC; with no peer launched the step barrier times out (200 ms) and the
-    # launch carries on unsynchronised: rank 0 writes its chunks into every PEER's recv[0] slot only
+    # AUTO + all peers at this size = PUSH_TMA (no barrier): rank 0 writes
+    # its chunks into every PEER's recv[0] slot only
     host0, host1 = wins[0].cpu().numpy(), wins[1].cpu().numpy()
     assert not host0[0:g * S].any(), "-2 must not touch the local slot (and a push lands nothing at home)"
     assert host1[0:S].any() and not host1[S:g * S].any()
@@ -91,6 +91,26 @@ def test_only_peer_selectors(env):
     host0 = wins[0].cpu().numpy()
     assert host0[S:2 * S].any() and not host0[0:S].any() and not host0[2 * S:g * S].any()
     assert (host0[S:2 * S] == host1[(g + 0) * S:(g + 1) * S]).all()
+    # PUSH_SYNC launched by ONE rank only: nobody answers the step barrier, the wait times out (20 ms here, 200 ms by
+    # default) and the launch carries on unsynchronised — a peer that never launched costs time, never a hang
+    import os
+    import time
+
+    for w in wins:
+        w[:g * S] = 0
+    os.environ["B200PROBE_A2A_SYNC_TIMEOUT_US"] = "20000"
+    try:
+        t0 = time.perf_counter()
+        p._check(p.lib.b200probe_a2a_exchange(0, 0, g, peers, S, SEED, 7, 0, -2, st0), "lonely sync")
+        torch.cuda.synchronize(0)
+        assert time.perf_counter() - t0 < 5.0
+    finally:
+        os.environ.pop("B200PROBE_A2A_SYNC_TIMEOUT_US", None)
+    assert not wins[0][:g * S].any().item()
+    for r in range(1, g):
+        got = wins[r].cpu().numpy()
+        assert np.array_equal(got[0:S].view(np.uint32), _oracle.pattern(o, 0, S // 4, o.oracle_a2a_chunk_seed(SEED, 0, r)))
+        assert not got[S:g * S].any()
     from k3s_nvidia_b200.probe import ProbeError
     with pytest.raises(ProbeError):
         p._check(p.lib.b200probe_a2a_exchange(0, 0, g, peers, S + 4, SEED, 0, 0, -1, st0), "bad S")
