@@ -137,7 +137,7 @@ def test_single_process_probe_verifies_and_reports(env, mode, variant):
             row = [rep.pair_gbs[i][j] for j in range(g) if j != i]
             assert min(row) > 1.5 * rep.egress_gbs[i] / max(g - 1, 2) or g == 2
             total_ms = sum((8 << 20) / (x * 1e6) for x in row)
-            assert 0.5 * rep.ms_median < total_ms < 1.5 * rep.ms_median
+            assert 0.3 * rep.ms_median < total_ms < 1.5 * rep.ms_median
 
 
 def test_full_size_exchange_properties(env):
