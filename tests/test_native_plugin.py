@@ -867,3 +867,33 @@ def test_unshared_config_and_index_strategy(tmp_path):
     finally:
         daemon.stop()
         kubelet.stop()
+
+
+def test_probe_round_without_a_gpu_publishes_unhealthy_like_the_python_runner(tmp_path, monkeypatch):
+    """GPU-less box: every active probe fails with B200PROBE_ENOCUDA (no CPU fallback anywhere) and both hosts publish
+    the same feature file — probes unhealthy, gate false, passive NVLink view (mock NVML) still reported."""
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from k3s_nvidia_b200 import labels as L
+    from k3s_nvidia_b200.probe import Probe
+
+    env = dict(os.environ, MOCK_NVML_DEVICES="2", MOCK_NVML_LINKS_DOWN="1:4")
+    out = subprocess.run([BIN, "--probe-once", "--features-dir", str(tmp_path / "native"), "--nvml-path", _oracle.MOCK_NVML], env=env,
+                         capture_output=True, text=True, timeout=60)
+    assert out.returncode == 0, out.stderr
+    assert "no CPU fallback" in out.stderr
+    native = L.parse_feature_file(out.stdout)
+    assert native == L.parse_feature_file(open(tmp_path / "native" / "b200probe").read())
+    monkeypatch.setenv("MOCK_NVML_DEVICES", "2")
+    monkeypatch.setenv("MOCK_NVML_LINKS_DOWN", "1:4")
+    p = Probe(_oracle.MOCK_NVML)
+    try:
+        py = L.ActiveProbeRunner(p, features_dir=str(tmp_path / "py"), interval_s=3600).run_once()
+    finally:
+        p.close()
+    native.pop("nvidia.com/b200probe.timestamp")
+    py.pop("nvidia.com/b200probe.timestamp")
+    assert native == py
+    assert native["nvidia.com/b200probe.healthy"] == "false" and native["nvidia.com/b200probe.gpu1.nvlink-links-ok"] == "false"
