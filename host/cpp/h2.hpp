@@ -171,7 +171,21 @@ public:
     Connection(int fd, const std::map<std::string, Route>* routes) : fd_(fd), routes_(routes) {}
     // The descriptor is closed only here, after the reader thread was joined by the owner and the workers by
     // join_streams(): closing a descriptor another thread is blocked on is a race (and a reuse hazard).
-    ~Connection() { close_fd(); join_streams(); const int fd = fd_.exchange(-1); if (fd >= 0) ::close(fd); }
+    ~Connection() {
+        close_fd();
+        join_streams();
+        const int fd = fd_.exchange(-1);
+        if (fd < 0) return;
+        // Closing a unix socket with unread bytes resets the peer and drops what we queued for it (a GOAWAY it has
+        // not read yet): swallow what is left, briefly, before closing.
+        char sink[4096];
+        for (int spins = 0; spins < 10; ++spins) {
+            struct pollfd pf = {fd, POLLIN, 0};
+            if (::poll(&pf, 1, 20) <= 0) break;
+            if (::recv(fd, sink, sizeof(sink), MSG_DONTWAIT) <= 0) break;
+        }
+        ::close(fd);
+    }
 
     // Any thread: wake everything that waits on this connection and make further I/O fail.  Does not close.
     void close_fd() {
