@@ -423,7 +423,7 @@ int get_encode(EncodeTiledFn* fn) {
 
 // [rows][k] bf16 row-major -> box {64 (k), box_rows}, 128B swizzle
 int make_map(CUtensorMap* map, const void* base, int rows, int k, int box_rows) {
-    EncodeTiledFn enc;
+    EncodeTiledFn enc = nullptr;
     int rc = get_encode(&enc);
     if (rc) return rc;
     cuuint64_t dims[2] = {(cuuint64_t)k, (cuuint64_t)rows};
