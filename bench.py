@@ -39,7 +39,19 @@ METRIC = "health-probe HBM GB/s & NVLink GB/s vs peak per GPU at 1/2/4/8 B200"
 WORKLOAD = "configs[1]: single-B200 HBM bandwidth probe, copy pass at the 1 GiB verdict size of the 1 MiB-1 GiB sweep"
 NVLINK_NOMINAL = 900.0
 A2A_VARIANT = int(os.environ.get("B200PROBE_A2A_VARIANT", "0"))   # 0 AUTO (= PUSH_SYNC for the exchange), 1 PULL_TMA, 2 PUSH_TMA, 3 PUSH_DIRECT, 4 PUSH_BUF, 5 MIX_TMA, 6 PUSH_STAGGER, 7 PUSH_SYNC
-NVLINK_MEASURED = 770.0   # /opt/skills/guides/B200_PROFILING.md, peer copy per direction
+NVLINK_GUIDE_ONE_WAY = 770.0   # /opt/skills/guides/B200_PROFILING.md: peer copy, ONE direction loaded; context only — the denominator
+                               # used here is the two-way copy-engine exchange measured in the same run (nvlink.plugin_entry.copy_engines)
+
+
+def cpu_model() -> str:
+    try:
+        with open("/proc/cpuinfo") as f:
+            for line in f:
+                if line.startswith("model name"):
+                    return line.split(":", 1)[1].strip()
+    except OSError:
+        pass
+    return "unknown"
 
 
 def measured_peaks():
@@ -112,11 +124,12 @@ def load_oracle():
 
 
 def cpu_copy_sample(o, threads: int, sample_bytes: int, target_s: float):
-    """Time the oracle port of the copy pass on host memory: calibrate, then ~target_s of work."""
+    """Time the oracle port of the copy pass on host memory: calibrate, then ~target_s of work.  Thread t is pinned to the
+    t-th CPU of the process's allowed set, so a slice is first-touched and copied on one NUMA node every pass."""
     s, x = C.c_uint64(), C.c_uint32()
-    t1 = o.oracle_host_sweep(sample_bytes, threads, 4, 2, 0xB200, C.byref(s), C.byref(x)) / 2
+    t1 = o.oracle_host_sweep_pinned(sample_bytes, threads, 4, 2, 0xB200, C.byref(s), C.byref(x)) / 2
     reps = max(3, min(2000, int(target_s / max(t1, 1e-4))))
-    dt = o.oracle_host_sweep(sample_bytes, threads, 4, reps, 0xB200, C.byref(s), C.byref(x))
+    dt = o.oracle_host_sweep_pinned(sample_bytes, threads, 4, reps, 0xB200, C.byref(s), C.byref(x))
     gbs = 2.0 * sample_bytes * reps / dt / 1e9
     return gbs, reps, dt, (s.value, x.value)
 
@@ -128,14 +141,23 @@ def nvml_poll_timing(o):
     try:
         if o.oracle_ph_open(None, None) != 0:
             return None
+        pinned_cpu = o.oracle_pin_self(0)                 # the single-thread figures are quoted pinned to one core
         o.oracle_ph_time_enumerate(10)
         o.oracle_ph_time_poll(10, 0)
         enum_us = o.oracle_ph_time_enumerate(1000)
         poll_us = o.oracle_ph_time_poll(1000, 0)
+        out = {"enumerate_us": round(enum_us, 2), "poll_us": round(poll_us, 2), "polls_per_s": round(1e6 / max(poll_us, 1e-9)),
+               "iters": 1000, "warmup": 10, "threads": 1, "pinned_to_cpu": pinned_cpu, "cpu_model": cpu_model(),
+               "host_cpus": os.cpu_count(), "allowed_cpus": o.oracle_allowed_cpus()}
+        # N-thread variant: one thread per GPU, each with its own event set on its device
+        pps = C.c_double()
+        n_gpus = len(_oracle_verdicts(o))
+        us_n = o.oracle_ph_time_poll_threads(min(n_gpus, os.cpu_count() or 1), 1000, C.byref(pps))
+        if us_n > 0:
+            out["per_gpu_threads"] = {"threads": min(n_gpus, os.cpu_count() or 1), "poll_us": round(us_n, 2), "polls_per_s": round(pps.value)}
         o.oracle_ph_close()
-        out = {"enumerate_us": round(enum_us, 2), "poll_us": round(poll_us, 2), "iters": 1000, "warmup": 10, "threads": 1}
     except Exception:  # noqa: BLE001
-        return None
+        return out
     try:
         import pynvml as nv
 
@@ -158,6 +180,13 @@ def nvml_poll_timing(o):
     return out
 
 
+def _oracle_verdicts(o):
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import _oracle
+
+    return _oracle.verdicts(o)
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -166,18 +195,21 @@ def run_reference(args):
     cores = os.cpu_count() or 1
     sample_bytes = GIB
     s, x = C.c_uint64(), C.c_uint32()
-    per = o.oracle_host_sweep(sample_bytes, cores, 4, 2, 0xB200, C.byref(s), C.byref(x)) / 2
+    cores = o.oracle_allowed_cpus()
+    sweep = o.oracle_host_sweep_pinned
+    per = sweep(sample_bytes, cores, 4, 2, 0xB200, C.byref(s), C.byref(x)) / 2
     if per * (args.steps + args.warmup) > 150.0:
         sample_bytes = 256 << 20
-        per = o.oracle_host_sweep(sample_bytes, cores, 4, 2, 0xB200, C.byref(s), C.byref(x)) / 2
+        per = sweep(sample_bytes, cores, 4, 2, 0xB200, C.byref(s), C.byref(x)) / 2
     steps = args.steps
     if per * (steps + args.warmup) > 150.0:
         steps = max(1, int(150.0 / per) - args.warmup)
     if args.warmup:
-        o.oracle_host_sweep(sample_bytes, cores, 4, args.warmup, 0xB200, C.byref(s), C.byref(x))
-    dt = o.oracle_host_sweep(sample_bytes, cores, 4, steps, 0xB200, C.byref(s), C.byref(x))
+        sweep(sample_bytes, cores, 4, args.warmup, 0xB200, C.byref(s), C.byref(x))
+    dt = sweep(sample_bytes, cores, 4, steps, 0xB200, C.byref(s), C.byref(x))
     gbs = 2.0 * sample_bytes * steps / dt / 1e9
-    sample = f"copy pass over {sample_bytes >> 20} MiB of host memory per step, {steps} steps, {cores} pthreads (oracle port; the reference ships no code)"
+    sample = (f"copy pass over {sample_bytes >> 20} MiB of host memory per step, {steps} steps, {cores} pthreads each pinned to one CPU "
+              f"({cpu_model()}; first touch and every pass of a slice on the same core) (oracle port; the reference ships no code)")
     line = {
         "impl": "reference", "metric": METRIC, "value": round(gbs, 2), "unit": "GB/s", "n_gpus": args.gpus, "steps": steps,
         "warmup": args.warmup, "ms_per_step": round(dt / steps * 1e3, 4), "higher_is_better": True, "scaling": "weak",
@@ -238,12 +270,20 @@ def run_ours(args):
     torch.cuda.synchronize()
     D.barrier()
     ms_local = e0.elapsed_time(e1)
-    # keep the GPU loaded until the sampler has something to report (outside the timed region)
-    t_end = time.time() + 0.3
-    while len(sampler.samples) < 8 and time.time() < t_end:
-        step()
-        torch.cuda.synchronize()
+    # sustained window next to the K-step figure (outside the timed region): back-to-back launches for >= 1 s, in batches of
+    # 256 launches between two events; the clock sampler keeps running, so its summary covers a second of load
+    sus_ms, sus_n = 0.0, 0
+    while sus_ms < 1000.0:
+        a_, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a_.record()
+        for _ in range(256):
+            step()
+        b_.record()
+        b_.synchronize()
+        sus_ms += a_.elapsed_time(b_)
+        sus_n += 256
     sampler.stop()
+    sustained = D.aggregate_bandwidth(2.0 * nbytes * sus_n, sus_ms)
     agg = D.aggregate_bandwidth(2.0 * nbytes * args.steps, ms_local)
     launch_ms = ms_local / args.steps
 
@@ -275,6 +315,12 @@ def run_ours(args):
     nvlink = None
     if world > 1:
         nvlink = nvlink_exchange(torch, D, p, local_rank, rank, world, stream, args)
+        # the code the DAEMON runs: one process driving all GPUs through b200probe_nvlink_a2a.  Rank 0 alone; the other ranks
+        # wait on a CPU-side barrier so that nothing of theirs sits on the SMs the exchange kernels need.
+        D.host_barrier()
+        if rank == 0:
+            nvlink["plugin_entry"] = nvlink_plugin_entry(p, world)
+        D.host_barrier()
 
     # ---- rank 0 extras: read/write legs, host-buffer round trip, CPU baseline ---------------------
     line = None
@@ -307,6 +353,8 @@ def run_ours(args):
         p.lib.b200probe_hbm_release(local_rank)
 
         peaks, peak_src = measured_peaks()
+        gemm = None if args.no_gemm else gemm_leg(torch, p, local_rank, nvml_index, peaks, sampler)
+        probe_round = None if args.no_probe_round else probe_round_leg(p)
         traffic = None
         try:
             with open(os.path.join(ROOT, "profiles", "roofline_traffic.json")) as f:
@@ -317,10 +365,10 @@ def run_ours(args):
         parity = None
         if world == 1 and not args.no_cpu_baseline:
             _, o = load_oracle()
-            cores = os.cpu_count() or 1
+            cores = o.oracle_allowed_cpus()
             gbs, reps, dt, chk = cpu_copy_sample(o, cores, GIB, 12.0)
-            cpu = {"value": round(gbs, 2), "unit": "GB/s", "cores": cores, "kind": "port",
-                   "sample": f"oracle port of the copy pass over 1 GiB of host memory, {reps} passes in {dt:.1f} s, {cores} pthreads",
+            cpu = {"value": round(gbs, 2), "unit": "GB/s", "cores": cores, "kind": "port", "cpu_model": cpu_model(),
+                   "sample": f"oracle port of the copy pass over 1 GiB of host memory, {reps} passes in {dt:.1f} s, {cores} pthreads each pinned to one CPU",
                    "reference_path_nvml": nvml_poll_timing(o)}
             parity = chk == got
         achieved = 2.0 * nbytes / (launch_ms * 1e-3) / 1e9
@@ -338,19 +386,35 @@ def run_ours(args):
                          "launch_ms": round(launch_ms, 5), "rank": 0},
             "e2e": {"value": round(e2e["gbs"], 2), "unit": "GB/s", "h2d_bytes_per_step": C.sizeof(L.HbmCfg) + 32, "d2h_bytes_per_step": 32,
                     "steps": e2e_steps, "ms_per_step": round(e2e["ms"] / e2e_steps, 4), "verified_every_step": bool(ok),
-                    "what": "b200probe_hbm_sweep(cfg on host) -> memset dst, copy kernel, device-side verify + checksum, D2H verdict; wall clock"},
+                    "what": "b200probe_hbm_sweep(cfg on host) -> memset dst, copy kernel, device-side verify + checksum, D2H verdict; wall clock",
+                    "hostbuf_value": round(hostbuf_gbs, 2),
+                    "hostbuf_what": "the same copy pass carrying HOST data (rank 0): pinned src -> H2D -> copy kernel + checksum -> D2H, 256 MiB each way per step; PCIe-bound (see e2e_hostbuf)"},
             "e2e_hostbuf": {"value": round(hostbuf_gbs, 2), "unit": "GB/s", "h2d_bytes_per_step": hb, "d2h_bytes_per_step": hb,
                             "roundtrip_identical": hostbuf_ok,
                             "what": "b200probe_hbm_copy_host: pinned host src -> H2D -> copy kernel + checksum -> D2H host dst, 8 MiB chunks pipelined on 3 streams (PCIe-bound: 2N bytes counted, N each way)"},
             "gpu_launches": args.steps * world,
             "clocks": sampler.summary(),
             "hbm_read_gbs": round(rd, 1), "hbm_write_gbs": round(wr, 1),
+            "hbm_sustained": {"value": round(sustained["gbs"], 2), "unit": "GB/s", "seconds": round(sustained["ms"] / 1e3, 3), "launches_per_rank": sus_n,
+                              "what": "the same copy launch back to back for >= 1 s after the timed K steps (aggregate over ranks, max-over-ranks time)"},
             "parity": {"dst_checksum_matches_oracle": parity, "sum64": f"{got[0]:#x}", "xor32": f"{got[1]:#x}"},
         }
         if cpu:
             line["cpu_baseline"] = cpu
+        if gemm:
+            line["roofline_gemm"] = gemm
+        if probe_round:
+            line["probe_round"] = probe_round
         if nvlink:
             line["nvlink"] = nvlink
+            ce = (nvlink.get("plugin_entry") or {}).get("copy_engines") or {}
+            line["roofline_nvlink"] = {
+                "bound": "nvlink", "achieved": nvlink["gbs_per_gpu_per_direction"], "peak": NVLINK_NOMINAL, "unit": "GB/s per direction per GPU",
+                "frac": round(nvlink["gbs_per_gpu_per_direction"] / NVLINK_NOMINAL, 4), "peak_source": "nominal 18 links x 50 GB/s (no NVLink figure in MEASURED_PEAKS.json)",
+                "measured_two_way_copy_engine_gbs": ce.get("gbs_per_gpu_per_direction"),
+                "frac_of_measured_two_way_copy": (round(nvlink["gbs_per_gpu_per_direction"] / ce["gbs_per_gpu_per_direction"], 4) if ce.get("gbs_per_gpu_per_direction") else None),
+                "guide_one_way_peer_copy_gbs": NVLINK_GUIDE_ONE_WAY, "kernel": nvlink["kernel"],
+                "algorithmic_bytes_per_launch": nvlink["algorithmic_bytes_per_gpu_per_direction"], "traffic": None}
     if rank == 0:
         emit(line)
     D.barrier()
@@ -435,9 +499,153 @@ def nvlink_exchange(torch, D, p, local_rank, rank, world, stream, args):
              3: "a2a_direct_kernel PUSH_DIRECT (16-byte stores on peer pointers)", 4: "a2a_ring_kernel PUSH_BUF"}
     return {"bytes_per_pair": S, "ms_per_exchange": round(ms, 4), "gbs_per_gpu_per_direction": round(per_dir, 1),
             "aggregate_gbs": round(per_dir * world, 1), "frac_of_nominal_900": round(per_dir / NVLINK_NOMINAL, 4),
-            "frac_of_measured_770": round(per_dir / NVLINK_MEASURED, 4), "verified": bool(ok), "steps": steps,
+            "verified": bool(ok), "steps": steps,
             "kernel": names.get(A2A_VARIANT, str(A2A_VARIANT)), "algorithmic_bytes_per_gpu_per_direction": (world - 1) * S,
             "scaling": "every rank moves (world-1)*S per exchange: total work grows with N"}
+
+
+def nvlink_plugin_entry(p, world):
+    """Rank 0, single process, all GPUs: b200probe_nvlink_a2a exactly as the plugin's active-probe round calls it (PEER_ALL,
+    verify), then the copy-engine leg (cudaMemcpyPeerAsync both ways) as the measured two-way peer-copy denominator."""
+    from k3s_nvidia_b200 import _lib as L
+
+    S = 256 << 20
+    ords = list(range(world))
+    out = {"bytes_per_pair": S, "gpus": world}
+    try:
+        t0 = time.perf_counter()
+        rep = p.nvlink_a2a(ords, bytes_per_pair=S, warmup=2, reps=5, verify=1)
+        wall = time.perf_counter() - t0
+        src = {L.PAIR_SHARE: "share of the concurrent exchange", L.PAIR_ISOLATED: "isolated pairs", L.PAIR_STEPPED: "drained, device-stamped steps (one pair per rank per step)"}
+        out.update({"gbs_per_gpu_per_direction": round(min(rep.egress_gbs[:world]), 1), "egress_min_max": [round(min(rep.egress_gbs[:world]), 1), round(max(rep.egress_gbs[:world]), 1)],
+                    "ms_median": round(rep.ms_median, 4), "pair_min": round(rep.min_pair_gbs, 1), "pair_max": round(rep.max_pair_gbs, 1),
+                    "pair_source": src.get(rep.pair_source, str(rep.pair_source)), "pair_max_le_900": rep.max_pair_gbs <= 900.0,
+                    "verified": rep.verified == 1, "call_wall_s": round(wall, 3)})
+        ce = p.nvlink_a2a(ords, bytes_per_pair=S, mode=L.A2A_CE, warmup=1, reps=5, verify=1)
+        out["copy_engines"] = {"gbs_per_gpu_per_direction": round(min(ce.egress_gbs[:world]), 1), "ms_median": round(ce.ms_median, 4), "verified": ce.verified == 1,
+                               "what": "cudaMemcpyPeerAsync of every chunk, all GPUs sending and receiving at once, same windows, same run"}
+    except Exception as e:  # noqa: BLE001
+        out["error"] = str(e)[:300]
+    finally:
+        try:
+            p.a2a_release()
+        except Exception:  # noqa: BLE001
+            pass
+    return out
+
+
+def gemm_leg(torch, p, ordinal, nvml_index, peaks, sampler):
+    """tcgen05 GEMM probe at 8192^3 for BOTH operand classes, and cuBLAS (torch.matmul) on the SAME device buffers in the
+    same process: burst = median / best of 10 single launches, sustained = back to back for 4 s (MEASURED_PEAKS.json's
+    protocol).  Data check: the library's own sampled fp64 check per class, and our C against cuBLAS's C on identical data."""
+    from k3s_nvidia_b200 import _lib as L
+
+    M = N = K = 8192
+    dev = torch.device("cuda", ordinal)
+    st = torch.cuda.current_stream().cuda_stream
+    A = torch.empty(M * K, dtype=torch.int16, device=dev)
+    B = torch.empty(N * K, dtype=torch.int16, device=dev)
+    Cm = torch.empty(M * N, dtype=torch.int16, device=dev)
+    Cl = torch.empty(M, N, dtype=torch.bfloat16, device=dev)
+    Ab, Bb = A.view(torch.bfloat16).view(M, K), B.view(torch.bfloat16).view(N, K)
+    flop = 2.0 * M * N * K
+
+    def ours():
+        p._check(p.lib.b200probe_gemm_launch(ordinal, A.data_ptr(), B.data_ptr(), Cm.data_ptr(), M, N, K, st), "gemm_launch")
+
+    def cublas():
+        torch.matmul(Ab, Bb.t(), out=Cl)
+
+    def burst(fn):
+        for _ in range(3):
+            fn()
+        ts = []
+        for _ in range(10):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            fn()
+            b.record()
+            b.synchronize()
+            ts.append(a.elapsed_time(b))
+        return flop / (statistics.median(ts) * 1e-3) / 1e12, flop / (min(ts) * 1e-3) / 1e12
+
+    def sustained(fn, seconds=4.0):
+        tot_ms, n = 0.0, 0
+        while tot_ms < seconds * 1e3:
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(100):
+                fn()
+            b.record()
+            b.synchronize()
+            tot_ms += a.elapsed_time(b)
+            n += 100
+        return flop * n / (tot_ms * 1e-3) / 1e12
+
+    out = {"bound": "tensor", "unit": "TFLOP/s", "shape": [M, N, K], "peak": peaks.get("bf16_tflops"), "peak_sustained": peaks.get("bf16_tflops_sustained"),
+           "kernel": "gemm_bf16_tn_2cta_kernel (tcgen05.mma cta_group::2, TMA loads, TMEM accumulators, TMA-store epilogue)",
+           "algorithmic_flop_per_launch": flop, "protocol": "burst: 10 single launches after 3 warm-ups (median, best); sustained: back to back for 4 s", "classes": {}}
+    for cls, name in ((L.GEMM_EXACT, "exact_k_over_128"), (L.GEMM_UNIFORM, "uniform_philox")):
+        p._check(p.lib.b200probe_gemm_fill(ordinal, A.data_ptr(), M * K, 0xB200, 0 | (cls << 1), st), "gemm_fill")
+        p._check(p.lib.b200probe_gemm_fill(ordinal, B.data_ptr(), N * K, 0xB200, 1 | (cls << 1), st), "gemm_fill")
+        torch.cuda.synchronize()
+        med, best = burst(ours)
+        lmed, lbest = burst(cublas)
+        sampler.start()
+        sus = sustained(ours)
+        clk = sampler.summary()
+        sampler.stop()
+        lsus = sustained(cublas)
+        ours()
+        cublas()
+        torch.cuda.synchronize()
+        diff = (Cm.view(torch.bfloat16).view(M, N).float() - Cl.float()).abs()
+        chk = p.gemm(nvml_index, warmup=1, reps=3, operands=cls)          # the library's own check (1024 samples vs fp64) on this class
+        out["classes"][name] = {
+            "ours": {"median": round(med, 1), "best": round(best, 1), "sustained_4s": round(sus, 1)},
+            "cublas_same_buffers": {"median": round(lmed, 1), "best": round(lbest, 1), "sustained_4s": round(lsus, 1)},
+            "ours_over_cublas": {"median": round(med / lmed, 4), "sustained_4s": round(sus / lsus, 4)},
+            "frac_of_measured_burst": round(med / peaks["bf16_tflops"], 4) if peaks.get("bf16_tflops") else None,
+            "frac_of_measured_sustained": round(sus / peaks["bf16_tflops_sustained"], 4) if peaks.get("bf16_tflops_sustained") else None,
+            "frac_of_nominal_2250": round(med / 2250.0, 4),
+            "clocks_during_sustained": clk,
+            "data": {"library_check_verified": chk.verified == 1, "samples": chk.samples, "bad": chk.bad, "max_err_over_tol": round(chk.max_err_over_tol, 4),
+                     "max_abs_diff_vs_cublas": float(diff.max().item()), "bit_identical_to_cublas": bool((diff == 0).all().item())},
+        }
+    p.lib.b200probe_gemm_release(ordinal)
+    u = out["classes"]["uniform_philox"]
+    out["achieved"] = u["ours"]["median"]                     # headline: SURVEY.md §8d's operand class
+    out["frac"] = u["frac_of_measured_burst"]
+    out["achieved_sustained"] = u["ours"]["sustained_4s"]
+    out["frac_sustained"] = u["frac_of_measured_sustained"]
+    return out
+
+
+def probe_round_leg(p):
+    """Wall time of ONE full active-probe round as the plugin daemon runs it (labels.ActiveProbeRunner.run_once: HBM sweep
+    256 MiB-1 GiB x 3 modes, GEMM 8192^3, passive NVLink status and, with >= 2 GPUs, the exchange; labels written to a
+    temporary features.d), cold (arenas allocated inside) and warm (second round)."""
+    import tempfile
+
+    from k3s_nvidia_b200.labels import ActiveProbeRunner, PREFIX
+
+    out = {}
+    try:
+        with tempfile.TemporaryDirectory() as d:
+            r = ActiveProbeRunner(p, features_dir=d, keep_arenas=True)
+            t0 = time.perf_counter()
+            labels = r.run_once()
+            out["cold_s"] = round(time.perf_counter() - t0, 3)
+            t0 = time.perf_counter()
+            labels = r.run_once()
+            out["warm_s"] = round(time.perf_counter() - t0, 3)
+            r.release()
+            out["gpus"] = p.device_count()
+            out["labels"] = len(labels)
+            out["gate"] = labels.get(f"{PREFIX}healthy")
+    except Exception as e:  # noqa: BLE001
+        out["error"] = str(e)[:300]
+    return out
 
 
 def main():
@@ -447,6 +655,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-gemm", action="store_true", help="skip the GEMM roofline leg (about 20 s)")
+    ap.add_argument("--no-probe-round", action="store_true", help="skip timing one full active-probe round")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3

@@ -6,15 +6,25 @@
 // reference hints at label gating in the commented selector of /root/reference/nvidia-smi.yaml:6-7 and says
 // the plugin "needs these labels for scheduling" (/root/reference/README.md:99).  We write a SECOND file in
 // the same directory with nvidia.com/b200probe.* keys, so no chart value changes.
+//
+// Tenants (values.yaml:16-18 time-slices every GPU four ways): a round first asks NVML who is on each device
+// (b200probe_device_busy) and SKIPS busy devices — probe-state=busy, the last idle verdict carried over, nothing of ours
+// touches the device; a failed device allocation (B200PROBE_ENOMEM) is handled the same way (no-memory), never as
+// unhealthy.  A GPU never measured has no verdict and the gate label is absent.  All probe arenas are released after
+// every round.  The file carries NFD's "# +expiry-time=" directive (now + 2 rounds) and is removed on a clean stop;
+// there is no timestamp label.  Gates follow this node's own first plausible healthy figures (calibration file).
 #pragma once
 #include <sys/stat.h>
 #include <unistd.h>
 
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <ctime>
+#include <fstream>
 #include <map>
+#include <set>
 #include <string>
 #include <thread>
 #include <vector>
@@ -99,21 +109,25 @@ inline Labels hbm_labels(const std::map<int, std::vector<b200probe_hbm_result_t>
     return out;
 }
 
-inline Labels nvlink_labels(const b200probe_a2a_result_t& rep, const std::vector<double>& pair_gbs, const Thresholds& th) {
+// ids[pos] = NVML index of the GPU at position pos of the exchange (the labels name NVML indices)
+inline Labels nvlink_labels(const b200probe_a2a_result_t& rep, const std::vector<double>& pair_gbs, const Thresholds& th, std::vector<int> ids = {}) {
     Labels out;
     const int G = rep.g;
+    if (ids.empty()) for (int i = 0; i < G; ++i) ids.push_back(i);
     bool ok = rep.verified != 0;
     const double min_gbs = th.nvlink_min_gbs > 0 ? th.nvlink_min_gbs : (G <= 2 ? 0.97 * kNvlinkHealthyPair : 0.96 * kNvlinkHealthyBox);
     double min_egress = 1e300;
-    for (int g = 0; g < G; ++g) {
-        out[key(g, "nvlink-egress-gbs")] = rint_str(rep.egress_gbs[g]);
-        out[key(g, "nvlink-ingress-gbs")] = rint_str(rep.ingress_gbs[g]);
-        const bool good = rep.egress_gbs[g] >= min_gbs;
+    for (int pos = 0; pos < G; ++pos) {
+        const int g = ids[(size_t)pos];
+        out[key(g, "nvlink-egress-gbs")] = rint_str(rep.egress_gbs[pos]);
+        out[key(g, "nvlink-ingress-gbs")] = rint_str(rep.ingress_gbs[pos]);
+        const bool good = rep.egress_gbs[pos] >= min_gbs;
         out[key(g, "nvlink-healthy")] = b(good && rep.verified != 0);
         ok = ok && good;
-        min_egress = std::min(min_egress, rep.egress_gbs[g]);
-        for (int p = 0; p < G; ++p)
-            if (p != g && pair_gbs[(size_t)(g * G + p)] > 0) out[key(g, ("nvlink-to-gpu" + std::to_string(p) + "-gbs").c_str())] = rint_str(pair_gbs[(size_t)(g * G + p)]);
+        min_egress = std::min(min_egress, rep.egress_gbs[pos]);
+        for (int q = 0; q < G; ++q)
+            if (q != pos && pair_gbs[(size_t)(pos * G + q)] > 0)
+                out[key(g, ("nvlink-to-gpu" + std::to_string(ids[(size_t)q]) + "-gbs").c_str())] = rint_str(pair_gbs[(size_t)(pos * G + q)]);
     }
     out[key("nvlink-min-pair-gbs")] = rint_str(rep.min_pair_gbs);
     out[key("nvlink-egress-pct-of-nominal")] = rint_str(100.0 * min_egress / kNvlinkNominal);
@@ -156,18 +170,77 @@ inline Labels gemm_labels(const std::map<int, b200probe_gemm_result_t>& per_gpu,
     return out;
 }
 
-// The one label manifests select on: every probe that ran is healthy.
+// The one label manifests select on: every probe that has a verdict is healthy.  No verdict at all -> no gate label.
 inline void gate_label(Labels* l) {
     bool any = false, all = true;
     for (const char* leaf : {"hbm-healthy", "nvlink-healthy", "gemm-healthy"}) {
         auto it = l->find(key(leaf));
         if (it != l->end()) { any = true; all = all && it->second == "true"; }
     }
-    (*l)[key("healthy")] = b(any && all);
+    if (any) (*l)[key("healthy")] = b(all);
 }
 
-inline std::string render(const Labels& l) {
+// join the active pair matrix with the passive per-link state to NAME the suspect (twin of
+// labels.py nvlink_localise: same reference = upper quartile of the matrix, same 90 % cold bar, same tie-breaks).
+inline Labels nvlink_localise(const b200probe_a2a_result_t& rep, const std::vector<double>& pair, const std::vector<int>& ids,
+                              const std::map<int, b200probe_nvlink_status_t>& passive) {
+    Labels out;
+    const int G = rep.g;
+    if (G < 2 || rep.pair_source == B200PROBE_PAIR_SHARE) return out;
+    struct Cell { double v; int i, j; };
+    std::vector<Cell> cells;
+    for (int i = 0; i < G; ++i) for (int j = 0; j < G; ++j) if (i != j && pair[(size_t)(i * G + j)] > 0) cells.push_back({pair[(size_t)(i * G + j)], i, j});
+    if (cells.empty()) return out;
+    std::vector<double> vals;
+    for (const auto& c : cells) vals.push_back(c.v);
+    std::sort(vals.begin(), vals.end());
+    const double ref = vals[(3 * (vals.size() - 1) + 3) / 4];
+    out[key("nvlink-pair-ref-gbs")] = rint_str(ref);
+    std::vector<Cell> cold;
+    for (const auto& c : cells) if (c.v < 0.9 * ref) cold.push_back(c);
+    if (cold.empty()) { out[key("nvlink-cold-cell")] = "none"; out[key("nvlink-suspect")] = "none"; return out; }
+    const Cell* worst = &cold[0];
+    for (const auto& c : cold) if (c.v < worst->v || (c.v == worst->v && (c.i < worst->i || (c.i == worst->i && c.j < worst->j)))) worst = &c;
+    out[key("nvlink-cold-cell")] = "gpu" + std::to_string(ids[(size_t)worst->i]) + "-to-gpu" + std::to_string(ids[(size_t)worst->j]);
+    out[key("nvlink-cold-cells")] = std::to_string(cold.size());
+    std::vector<int> row((size_t)G, 0), col((size_t)G, 0);
+    for (const auto& c : cold) { row[(size_t)c.i]++; col[(size_t)c.j]++; }
+    auto links_down = [&](int g) {
+        auto it = passive.find(ids[(size_t)g]);
+        return it != passive.end() && it->second.links_total > 0 && it->second.links_active < it->second.links_total;
+    };
+    int best = 0;
+    for (int g = 1; g < G; ++g) {
+        const int sb = row[(size_t)best] + col[(size_t)best], sg = row[(size_t)g] + col[(size_t)g];
+        if (sg > sb || (sg == sb && links_down(g) && !links_down(best))) best = g;       // ties: links down first, then the lower position
+    }
+    if (row[(size_t)best] + col[(size_t)best] == 0) return out;
+    out[key("nvlink-suspect")] = "gpu" + std::to_string(ids[(size_t)best]);
+    const int r = row[(size_t)best], c = col[(size_t)best], half = (G - 1 + 1) / 2;
+    if (links_down(best)) {
+        const auto& st = passive.at(ids[(size_t)best]);
+        const uint32_t mask = (uint32_t)(((1ull << st.links_total) - 1) & ~(uint64_t)st.active_mask);
+        char hex[32];
+        snprintf(hex, sizeof(hex), "0x%x", mask);
+        out[key("nvlink-suspect-evidence")] = "links-down";
+        out[key(ids[(size_t)best], "nvlink-links-down-mask")] = hex;
+    } else if (G > 2 && r >= half && c >= half) out[key("nvlink-suspect-evidence")] = "port-both-directions";
+    else if (G > 2 && r > c && r >= 2) out[key("nvlink-suspect-evidence")] = "egress-cold";
+    else if (G > 2 && c > r && c >= 2) out[key("nvlink-suspect-evidence")] = "ingress-cold";
+    else out[key("nvlink-suspect-evidence")] = "pair-only";
+    return out;
+}
+
+inline std::string render(const Labels& l, double expiry_unix = 0) {
     std::string text;
+    if (expiry_unix > 0) {               // NFD local source [RECALLED, NFD >= 0.14]: the labels of this file are dropped after this instant
+        const time_t t = (time_t)expiry_unix;
+        struct tm tmv;
+        gmtime_r(&t, &tmv);
+        char buf[64];
+        strftime(buf, sizeof(buf), "%Y-%m-%dT%H:%M:%SZ", &tmv);
+        text += std::string("# +expiry-time=") + buf + "\n";
+    }
     for (const auto& kv : l) {                                         // std::map iterates sorted by key, like sorted(labels.items())
         if (!valid_label(kv.first, kv.second)) throw std::runtime_error("invalid label: " + kv.first + "=" + kv.second);
         text += kv.first + "=" + kv.second + "\n";
@@ -176,11 +249,14 @@ inline std::string render(const Labels& l) {
 }
 
 // Atomic replace (NFD may read at any time): write a hidden temp file, then rename.
-inline std::string write_feature_file(const Labels& l, const std::string& dir, const std::string& name = "b200probe") {
-    std::string cur;
+inline void mkdirs(const std::string& dir) {
     for (size_t i = 1; i <= dir.size(); ++i)
-        if (i == dir.size() || dir[i] == '/') { cur = dir.substr(0, i); ::mkdir(cur.c_str(), 0755); }
-    const std::string text = render(l);
+        if (i == dir.size() || dir[i] == '/') ::mkdir(dir.substr(0, i).c_str(), 0755);
+}
+
+inline std::string write_feature_file(const Labels& l, const std::string& dir, const std::string& name = "b200probe", double expiry_unix = 0) {
+    mkdirs(dir);
+    const std::string text = render(l, expiry_unix);
     std::string tmpl = dir + "/.b200probe.XXXXXX";                       // dot-files are ignored by NFD
     std::vector<char> tmp(tmpl.begin(), tmpl.end());
     tmp.push_back(0);
@@ -199,12 +275,43 @@ inline std::string write_feature_file(const Labels& l, const std::string& dir, c
     return path;
 }
 
-// Runs the active probes on every enumerated GPU at an interval and publishes the labels.  A probe that
-// fails (CUDA error, data mismatch) publishes ...healthy=false; it never blocks ListAndWatch.
+// This node's own healthy figures (first plausible healthy round), key=value lines under the state directory; twin of
+// labels.py Calibration: accepted once, when within 15 % of the pool figure; the gate is then a fraction of THAT.
+class Calibration {
+public:
+    explicit Calibration(const std::string& state_dir) : path_(state_dir + "/calibration"), dir_(state_dir) {
+        std::ifstream f(path_);
+        std::string line;
+        while (std::getline(f, line)) {
+            const size_t eq = line.find('=');
+            if (line.empty() || line[0] == '#' || eq == std::string::npos) continue;
+            char* end = nullptr;
+            const double v = strtod(line.c_str() + eq + 1, &end);
+            if (end && end != line.c_str() + eq + 1) vals_[line.substr(0, eq)] = v;
+        }
+    }
+    double get(const std::string& k, double pool) const { auto it = vals_.find(k); return it == vals_.end() ? pool : it->second; }
+    void offer(const std::string& k, double value, double pool) {
+        if (vals_.count(k) || value < 0.85 * pool || value > 1.15 * pool) return;
+        vals_[k] = value;
+        mkdirs(dir_);
+        const std::string tmp = path_ + ".tmp";
+        { std::ofstream f(tmp); char buf[64]; for (const auto& kv : vals_) { snprintf(buf, sizeof(buf), "%.1f", kv.second); f << kv.first << "=" << buf << "\n"; } }
+        ::rename(tmp.c_str(), path_.c_str());
+    }
+private:
+    std::string path_, dir_;
+    std::map<std::string, double> vals_;
+};
+
+// Runs the active probes on every enumerated, IDLE GPU at an interval and publishes the labels.  A probe that fails for a
+// reason of the GPU (CUDA error, data mismatch, too slow) publishes ...healthy=false; a GPU that is in use or has no memory
+// to spare is skipped and keeps its last idle verdict.  Never blocks ListAndWatch; holds no device memory between rounds.
 class ActiveProbeRunner {
 public:
-    ActiveProbeRunner(const std::string& features_dir, double interval_s, bool run_nvlink = true, bool run_gemm = true)
-        : dir_(features_dir), interval_s_(interval_s), run_nvlink_(run_nvlink), run_gemm_(run_gemm) {}
+    ActiveProbeRunner(const std::string& features_dir, double interval_s, bool run_nvlink = true, bool run_gemm = true, bool keep_arenas = false)
+        : dir_(features_dir), interval_s_(interval_s), run_nvlink_(run_nvlink), run_gemm_(run_gemm), keep_arenas_(keep_arenas),
+          cal_(getenv("B200PROBE_STATE_DIR") && *getenv("B200PROBE_STATE_DIR") ? std::string(getenv("B200PROBE_STATE_DIR")) : features_dir + "/.b200probe-state") {}
     ~ActiveProbeRunner() { stop(); }
 
     Labels run_once() {
@@ -213,52 +320,93 @@ public:
         b200probe_device_count(&n);
         std::vector<b200probe_device_t> infos((size_t)n);
         for (int i = 0; i < n; ++i) b200probe_device_info(i, &infos[(size_t)i]);
-
-        std::map<int, std::vector<b200probe_hbm_result_t>> hbm;
-        bool hbm_failed = false;
+        // who is on the devices?  asked once, before any probe of ours shows up in the utilisation figures
+        std::map<int, std::string> state;
         for (const auto& d : infos) {
+            b200probe_busy_t busy;
+            state[d.index] = (b200probe_device_busy(d.index, &busy) == 0 && busy.busy) ? "busy" : "probed";
+        }
+        const bool explicit_hbm = getenv("B200PROBE_HBM_MIN_GBS") != nullptr, explicit_gemm = getenv("B200PROBE_GEMM_MIN_TFLOPS") != nullptr;
+
+        for (const auto& d : infos) {
+            if (state[d.index] != "probed") continue;
             b200probe_hbm_cfg_t cfg;
             memset(&cfg, 0, sizeof(cfg));
             cfg.min_bytes = 1ull << 28; cfg.max_bytes = 1ull << 30; cfg.warmup = 2; cfg.reps = 5; cfg.verify = 1;
             std::vector<b200probe_hbm_result_t> pts(128);
             int got = 0;
             const int rc = b200probe_hbm_sweep(d.index, &cfg, pts.data(), (int)pts.size(), &got);
-            if (rc) {
+            if (rc == B200PROBE_ENOMEM) {
+                state[d.index] = "no-memory";
+                plugin::logf("GPU %d: no device memory for the HBM probe (tenants hold it): inconclusive", d.index);
+            } else if (rc) {
                 plugin::logf("HBM probe failed on GPU %d: %s", d.index, b200probe_strerror(rc));
                 l[key(d.index, "hbm-healthy")] = "false";
-                hbm_failed = true;
-            } else { pts.resize((size_t)got); hbm[d.index] = pts; }
+            } else {
+                pts.resize((size_t)got);
+                Thresholds th = th_;
+                const std::string ck = std::string("hbm-copy-gbs.") + d.uuid;
+                if (!explicit_hbm) th.hbm_min_gbs = 0.90 * cal_.get(ck, kHbmMeasured);
+                std::map<int, std::vector<b200probe_hbm_result_t>> one;
+                one[d.index] = pts;
+                Labels gl = hbm_labels(one, th);
+                for (const auto& kv : gl) if (is_gpu_key(kv.first)) l[kv.first] = kv.second;
+                auto h = gl.find(key(d.index, "hbm-healthy")), c = gl.find(key(d.index, "hbm-copy-gbs"));
+                if (h != gl.end() && h->second == "true" && c != gl.end()) cal_.offer(ck, atof(c->second.c_str()), kHbmMeasured);
+            }
         }
-        if (!hbm.empty()) {
-            Labels got = hbm_labels(hbm, th_);
-            for (const auto& kv : got) if (!(l.count(kv.first) && l[kv.first] == "false")) l[kv.first] = kv.second;
-        }
-        if (hbm_failed) l[key("hbm-healthy")] = "false";
-
         if (run_gemm_) {
-            std::map<int, b200probe_gemm_result_t> gemm;
-            bool failed = false;
             for (const auto& d : infos) {
+                if (state[d.index] != "probed") continue;
                 b200probe_gemm_cfg_t cfg;
                 memset(&cfg, 0, sizeof(cfg));
                 cfg.warmup = 2; cfg.reps = 5;
                 b200probe_gemm_result_t r;
                 const int rc = b200probe_gemm(d.index, &cfg, &r);
-                if (rc) {
+                if (rc == B200PROBE_ENOMEM) state[d.index] = "no-memory";
+                else if (rc) {
                     plugin::logf("GEMM probe failed on GPU %d: %s", d.index, b200probe_strerror(rc));
                     l[key(d.index, "gemm-healthy")] = "false";
-                    failed = true;
-                } else gemm[d.index] = r;
+                } else {
+                    Thresholds th = th_;
+                    const std::string ck = std::string("gemm-tflops.") + d.uuid;
+                    if (!explicit_gemm) th.gemm_min_tflops = 0.70 * cal_.get(ck, kGemmMeasured);
+                    std::map<int, b200probe_gemm_result_t> one;
+                    one[d.index] = r;
+                    Labels gl = gemm_labels(one, th);
+                    for (const auto& kv : gl) if (is_gpu_key(kv.first)) l[kv.first] = kv.second;
+                    auto h = gl.find(key(d.index, "gemm-healthy"));
+                    if (h != gl.end() && h->second == "true") cal_.offer(ck, r.tflops_median, kGemmMeasured);
+                }
             }
-            if (!gemm.empty()) { Labels got = gemm_labels(gemm, th_); for (const auto& kv : got) l[kv.first] = kv.second; }
-            if (failed) l[key("gemm-healthy")] = "false";
+        }
+        // GPUs that were skipped keep what their last measured round said
+        for (const auto& d : infos) {
+            l[key(d.index, "probe-state")] = state[d.index];
+            if (state[d.index] != "probed") { carry(&l, d.index, "hbm-"); carry(&l, d.index, "gemm-"); }
+        }
+        aggregate(&l, "hbm-healthy");
+        if (run_gemm_) aggregate(&l, "gemm-healthy");
+        {
+            bool have = false;
+            double mn = 0;
+            for (const auto& kv : l) {
+                int g; std::string leaf;
+                if (split_gpu_key(kv.first, &g, &leaf) && leaf == "hbm-copy-gbs") { const double v = atof(kv.second.c_str()); mn = have ? std::min(mn, v) : v; have = true; }
+            }
+            if (have) l[key("hbm-copy-min-gbs")] = rint_str(mn);
         }
 
-        std::vector<int> ords;
-        for (int i = 0; i < n; ++i) { b200probe_device_t d; if (b200probe_device_info(i, &d) == 0 && d.cuda_ordinal >= 0) ords.push_back(d.cuda_ordinal); }
+        // ---- NVLink: passive state of every GPU, the exchange over the idle ones ----
         std::map<int, b200probe_nvlink_status_t> before;
         for (const auto& d : infos) { b200probe_nvlink_status_t st; if (b200probe_nvlink_passive(d.index, &st) == 0) before[d.index] = st; }
         { Labels got = nvlink_passive_labels(before); for (const auto& kv : got) l[kv.first] = kv.second; }
+        std::vector<int> ords, ids;
+        for (int i = 0; i < n; ++i) {
+            b200probe_device_t d;
+            if (b200probe_device_info(i, &d) == 0 && d.cuda_ordinal >= 0 && state[d.index] == "probed") { ords.push_back(d.cuda_ordinal); ids.push_back(d.index); }
+        }
+        bool ran_nvlink = false;
         if (run_nvlink_ && ords.size() >= 2) {
             const int G = (int)ords.size();
             b200probe_a2a_cfg_t cfg;
@@ -267,32 +415,55 @@ public:
             std::vector<double> pair((size_t)(G * G), 0.0);
             b200probe_a2a_result_t rep;
             const int rc = b200probe_nvlink_a2a(ords.data(), G, &cfg, pair.data(), &rep);
-            if (rc) {
+            if (rc == B200PROBE_ENOMEM) {
+                plugin::logf("no device memory for the NVLink exchange: inconclusive");
+            } else if (rc) {
                 plugin::logf("NVLink probe failed: %s", b200probe_strerror(rc));
                 l[key("nvlink-healthy")] = "false";
+                ran_nvlink = true;
             } else {
-                Labels got = nvlink_labels(rep, pair, th_);
+                ran_nvlink = true;
+                Labels got = nvlink_labels(rep, pair, th_, ids);
+                for (const auto& kv : got) l[kv.first] = kv.second;
+                got = nvlink_localise(rep, pair, ids, before);
                 for (const auto& kv : got) l[kv.first] = kv.second;
                 auto it = l.find(key("nvlink-links-ok"));
                 if (it != l.end() && it->second == "false") l[key("nvlink-healthy")] = "false";   // a dead link fails the gate even if the matrix clears the bar
                 double min_eff = 2.0;
-                for (const auto& kv : before) {
+                for (int idx : ids) {
+                    auto bi = before.find(idx);
                     b200probe_nvlink_status_t after;
-                    if (b200probe_nvlink_passive(kv.first, &after) != 0 || !kv.second.counters_ok || !after.counters_ok) continue;
-                    const double dd = (double)(after.data_tx_kib - kv.second.data_tx_kib), rr = (double)(after.raw_tx_kib - kv.second.raw_tx_kib);
+                    if (bi == before.end() || b200probe_nvlink_passive(idx, &after) != 0 || !bi->second.counters_ok || !after.counters_ok) continue;
+                    const double dd = (double)(after.data_tx_kib - bi->second.data_tx_kib), rr = (double)(after.raw_tx_kib - bi->second.raw_tx_kib);
                     if (rr > 0 && dd > 0) min_eff = std::min(min_eff, dd / rr);
                 }
                 if (min_eff <= 1.0) l[key("nvlink-data-over-raw-pct")] = rint_str(100.0 * min_eff);
             }
         }
+        if (run_nvlink_ && !ran_nvlink) {
+            // nothing measured this round (GPUs busy / a single GPU): the whole NVLink picture of the last measured round stands
+            for (const auto& kv : last_)
+                if (kv.first.find("nvlink-") != std::string::npos && kv.first.find("nvlink-links-") == std::string::npos && !l.count(kv.first)) l[kv.first] = kv.second;
+        }
         gate_label(&l);
-        l[key("timestamp")] = std::to_string((long long)time(nullptr));
-        write_feature_file(l, dir_);
+        if (!keep_arenas_) release(infos);
+        last_ = l;
+        write_feature_file(l, dir_, "b200probe", (double)time(nullptr) + 2.0 * interval_s_ + 60.0);
         return l;
     }
 
+    // free every probe arena of this process (device memory, streams, NCCL communicators)
+    static void release(const std::vector<b200probe_device_t>& infos) {
+        for (const auto& d : infos) if (d.cuda_ordinal >= 0) { b200probe_hbm_release(d.cuda_ordinal); b200probe_gemm_release(d.cuda_ordinal); }
+        b200probe_a2a_release();
+    }
+
+    // clean shutdown: the verdicts are no longer maintained, so they are removed (NFD drops the labels)
+    void withdraw() { ::unlink((dir_ + "/b200probe").c_str()); }
+
     void start() {
         stop_ = false;
+        started_ = true;
         thread_ = std::thread([this] {
             while (!stop_) {
                 try { run_once(); } catch (const std::exception& e) { plugin::logf("active probe round failed: %s", e.what()); }
@@ -302,16 +473,47 @@ public:
         });
     }
     void stop() {
-        stop_ = true;
+        { std::lock_guard<std::mutex> lk(mu_); stop_ = true; }      // under the mutex: the loop cannot test the predicate and then miss the notify
         cv_.notify_all();
         if (thread_.joinable()) thread_.join();
+        if (started_) { withdraw(); started_ = false; }
     }
 
 private:
+    static bool split_gpu_key(const std::string& k, int* gpu, std::string* leaf) {
+        const std::string pfx = std::string(kPrefix) + "gpu";
+        if (k.compare(0, pfx.size(), pfx) != 0) return false;
+        size_t i = pfx.size();
+        if (i >= k.size() || !isdigit((unsigned char)k[i])) return false;
+        int g = 0;
+        while (i < k.size() && isdigit((unsigned char)k[i])) g = g * 10 + (k[i++] - '0');
+        if (i >= k.size() || k[i] != '.') return false;
+        *gpu = g; *leaf = k.substr(i + 1);
+        return true;
+    }
+    static bool is_gpu_key(const std::string& k) { int g; std::string leaf; return split_gpu_key(k, &g, &leaf); }
+    void carry(Labels* l, int idx, const char* leaf_prefix) const {
+        for (const auto& kv : last_) {
+            int g; std::string leaf;
+            if (split_gpu_key(kv.first, &g, &leaf) && g == idx && leaf.compare(0, strlen(leaf_prefix), leaf_prefix) == 0 && !l->count(kv.first)) (*l)[kv.first] = kv.second;
+        }
+    }
+    static void aggregate(Labels* l, const char* leaf_name) {
+        bool any = false, all = true;
+        for (const auto& kv : *l) {
+            int g; std::string leaf;
+            if (split_gpu_key(kv.first, &g, &leaf) && leaf == leaf_name) { any = true; all = all && kv.second == "true"; }
+        }
+        if (any) (*l)[key(leaf_name)] = b(all); else l->erase(key(leaf_name));
+    }
+
     std::string dir_;
     double interval_s_;
-    bool run_nvlink_, run_gemm_;
+    bool run_nvlink_, run_gemm_, keep_arenas_;
+    Calibration cal_;
     Thresholds th_;
+    Labels last_;
+    bool started_ = false;
     std::atomic<bool> stop_{false};
     std::mutex mu_;
     std::condition_variable cv_;

@@ -38,7 +38,7 @@
 extern "C" {
 #endif
 
-#define B200PROBE_ABI_VERSION 1
+#define B200PROBE_ABI_VERSION 2
 
 /* ---- status codes --------------------------------------------------------------------------- */
 #define B200PROBE_OK            0
@@ -112,6 +112,21 @@ int  b200probe_health_wait(int timeout_ms, b200probe_health_event_t* ev);
 int  b200probe_passive_health(int timeout_ms, uint64_t* unhealthy_mask);
 int  b200probe_health_mask(uint64_t* unhealthy_mask);
 void b200probe_health_close(void);
+
+/* ---- is the device in use by somebody else? ------------------------------------------------------
+ * The active probes are gated against idle-box figures and compete with tenants for SMs, HBM bandwidth and
+ * memory (values.yaml:16-18 time-slices every GPU four ways, so tenants are the normal case).  The host asks
+ * before a probe round and SKIPS a busy device (verdict "inconclusive", last idle verdict kept) — it never
+ * reports a loaded GPU as unhealthy.  compute_procs excludes the calling process (NVML reports host-namespace
+ * pids: a caller that has probed the device and cannot find its own pid is assumed to be one of the entries). */
+#define B200PROBE_BUSY_UTIL_PCT 10
+typedef struct b200probe_busy {
+    int      compute_procs;         /* nvmlDeviceGetComputeRunningProcesses_v3 minus this process; -1 = unreadable */
+    int      util_gpu_pct, util_mem_pct;   /* nvmlDeviceGetUtilizationRates (last sample period); -1 = unreadable  */
+    uint64_t mem_used;              /* nvmlDeviceGetMemoryInfo().used, bytes                                         */
+    int      busy;                  /* compute_procs > 0 || util_gpu_pct >= B200PROBE_BUSY_UTIL_PCT                  */
+} b200probe_busy_t;
+int b200probe_device_busy(int idx, b200probe_busy_t* out);
 
 /* ---- passive NVLink / fabric status ------------------------------------------- */
 typedef struct b200probe_nvlink_status {
@@ -201,6 +216,8 @@ int b200probe_host_free(void* ptr);
 #define B200PROBE_A2A_PEER_ALL    0   /* our peer-memory kernel, all pairs concurrently            */
 #define B200PROBE_A2A_PEER_PAIR   1   /* same kernel, one (src,dst) pair at a time -> matrix       */
 #define B200PROBE_A2A_NCCL        2   /* grouped ncclSend/ncclRecv (the library leg, for contrast) */
+#define B200PROBE_A2A_CE          3   /* cudaMemcpyPeerAsync of every chunk (copy engines; the second
+                                         library leg: the two-way peer-copy rate measured in the same run) */
 /* exchange kernels (cfg.variant) */
 #define B200PROBE_A2A_AUTO        0   /* one pair: PULL_TMA; concurrent exchange: PUSH_SYNC when G > 2 and
                                          S >= 64 MiB (128 MiB for free-running launches), else PUSH_TMA */
@@ -237,15 +254,25 @@ typedef struct b200probe_a2a_result {
     double   ingress_gbs[B200PROBE_MAX_DEVICES];
     double   min_pair_gbs, max_pair_gbs;
     int      verified;              /* 1 = every landed chunk equals the regenerated pattern        */
+    int      pair_source;           /* what pair_gbs holds: B200PROBE_PAIR_*                        */
 } b200probe_a2a_result_t;
+#define B200PROBE_PAIR_SHARE     0    /* egress / (g-1): the pair's share of a concurrent exchange    */
+#define B200PROBE_PAIR_ISOLATED  1    /* PEER_PAIR: the pair moved alone on an otherwise idle fabric  */
+#define B200PROBE_PAIR_STEPPED   2    /* PUSH_SYNC steps, each DRAINED before the next: S / (last store
+                                         complete - step start), every rank busy with one pair       */
 
 /* Single process, all GPUs (how the plugin daemon runs).  cuda_ordinals[g]; pair_gbs is g*g
  * row-major [src][dst], diagonal 0.  PEER_PAIR: each pair measured alone.  PEER_ALL: under PUSH_SYNC
- * the exchange moves one pair per step (src -> (src+t) mod g) and the kernel time-stamps the steps, so
- * the entry is that pair's own rate inside the full exchange; for the free-running schedules it is the
- * pair's share egress/(g-1). */
+ * the exchange moves one pair per step (src -> (src+t) mod g); after the timed exchanges three more
+ * run with every step drained and time-stamped on the device, and the entry is the median of that
+ * pair's own rate, first byte issued to last store complete (never above the port rate); for the
+ * free-running schedules it is the pair's share egress/(g-1).  out->pair_source says which.
+ * Windows, streams and NCCL communicators stay resident between calls with the same devices, S and
+ * seed; b200probe_a2a_release() frees them (the plugin does after every probe round).
+ * A failed device allocation returns B200PROBE_ENOMEM (a resource verdict, not a fault). */
 int b200probe_nvlink_a2a(const int* cuda_ordinals, int g, const b200probe_a2a_cfg_t* cfg,
                          double* pair_gbs, b200probe_a2a_result_t* out);
+int b200probe_a2a_release(void);
 
 /* Enable peer access between every ordered pair of the listed devices (idempotent). */
 int b200probe_enable_peer_access(const int* cuda_ordinals, int g);
@@ -275,11 +302,16 @@ int b200probe_a2a_exchange(int cuda_ordinal, int rank, int world, void* const* w
 uint32_t b200probe_a2a_chunk_seed(uint32_t seed, int src, int dst);
 
 /* ---- tcgen05 GEMM probe (row a13) --------------------------------------------------------------- */
+#define B200PROBE_GEMM_OPERANDS_EXACT    0   /* k/128, k integer in [-128,127]: every fp32 partial sum exact -> C bit-exact
+                                               against the fp64 contraction rounded once to bf16 (tolerance 0) */
+#define B200PROBE_GEMM_OPERANDS_UNIFORM  1   /* bf16 U(-1,1) from Philox4x32-10 under key (seed, 0); sampled
+                                               outputs within 2^-8 |ref| + 2^-10 sqrt(K) of the fp64 contraction        */
 typedef struct b200probe_gemm_cfg {
-    int      m, n, k;               /* 0 = 8192; multiples of 256/256/64                           */
+    int      m, n, k;               /* 0 = 8192; multiples of 128 (256 for the CTA-pair kernel)/256/64 */
     int      warmup, reps;          /* 0,0 = 3,10                                                  */
     uint32_t seed;
     int      samples;               /* sampled outputs checked against fp64 dot products; 0 = 1024 */
+    int      operands;              /* B200PROBE_GEMM_OPERANDS_*                                   */
     double   sustain_seconds;       /* >0: additionally run back to back for this long             */
 } b200probe_gemm_cfg_t;
 
@@ -291,16 +323,23 @@ typedef struct b200probe_gemm_result {
     int      samples, bad;                 /* bad = samples outside tolerance                      */
     uint64_t c_sum64; uint32_t c_xor32;    /* checksum of the bf16 C matrix (run-to-run identity)  */
     int      verified;
+    int      operands;                     /* the class that ran                                   */
+    double   max_err_over_tol;             /* UNIFORM: max |err| / tolerance over the samples (<= 1) */
 } b200probe_gemm_result_t;
 
+/* Operands and C stay resident per device between calls with the same shape, seed and operand class
+ * (b200probe_gemm_release frees them; a failed device allocation returns B200PROBE_ENOMEM). */
 int b200probe_gemm(int idx, const b200probe_gemm_cfg_t* cfg, b200probe_gemm_result_t* out);
+int b200probe_gemm_release(int cuda_ordinal);
 /* Resident launch: A [m][k] bf16 row-major, B [n][k] bf16 row-major (i.e. C = A * B^T),
  * C [m][n] bf16.  Asynchronous on stream. */
 int b200probe_gemm_launch(int cuda_ordinal, const void* a, const void* b, void* c,
                           int m, int n, int k, void* stream);
-/* Deterministic bf16 operand generator used by the probe and by the oracle:
- * element e of matrix `which` (0=A,1=B) = bf16(hash(seed,which,e) mapped to [-1,1)). */
+/* Deterministic bf16 operand generators used by the probe and restated by the oracle.
+ * which: bit 0 = matrix (0 = A, 1 = B), bit 1 = operand class (0 EXACT, 1 UNIFORM); dst 16-byte aligned.
+ * b200probe_gemm_operand_bits is the same function for one element on the host (the library's own check uses it). */
 int b200probe_gemm_fill(int cuda_ordinal, void* dst, uint64_t elems, uint32_t seed, int which, void* stream);
+uint16_t b200probe_gemm_operand_bits(uint64_t elem, uint32_t seed, int which);
 
 /* ---- data pattern (closed form shared by kernels, oracle and tests) ----------------------------- */
 /* word i of a buffer:  ((uint32_t)i * 2654435761u) ^ seed ^ (uint32_t)(i >> 32)                   */

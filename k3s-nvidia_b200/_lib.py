@@ -11,12 +11,15 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libb200probe.so")
 
+ABI_VERSION = 2
 MAX_DEVICES = 64
 IPC_HANDLE_BYTES = 64
 
 HBM_READ, HBM_WRITE, HBM_COPY = 1, 2, 4
 VARIANT_TMA, VARIANT_DIRECT = 0, 1
-A2A_PEER_ALL, A2A_PEER_PAIR, A2A_NCCL = 0, 1, 2
+A2A_PEER_ALL, A2A_PEER_PAIR, A2A_NCCL, A2A_CE = 0, 1, 2, 3
+PAIR_SHARE, PAIR_ISOLATED, PAIR_STEPPED = 0, 1, 2
+GEMM_EXACT, GEMM_UNIFORM = 0, 1
 A2A_AUTO, A2A_PULL_TMA, A2A_PUSH_TMA, A2A_PUSH_DIRECT, A2A_PUSH_BUF, A2A_MIX_TMA, A2A_PUSH_STAGGER, A2A_PUSH_SYNC = 0, 1, 2, 3, 4, 5, 6, 7
 A2A_SYNC_BYTES = 4096
 NVML_ERROR_TIMEOUT = 10
@@ -67,6 +70,16 @@ class NvlinkStatus(C.Structure):
         ("raw_tx_kib", C.c_uint64),
         ("raw_rx_kib", C.c_uint64),
         ("counters_ok", C.c_int),
+    ]
+
+
+class Busy(C.Structure):
+    _fields_ = [
+        ("compute_procs", C.c_int),
+        ("util_gpu_pct", C.c_int),
+        ("util_mem_pct", C.c_int),
+        ("mem_used", C.c_uint64),
+        ("busy", C.c_int),
     ]
 
 
@@ -128,6 +141,7 @@ class A2aResult(C.Structure):
         ("min_pair_gbs", C.c_double),
         ("max_pair_gbs", C.c_double),
         ("verified", C.c_int),
+        ("pair_source", C.c_int),
     ]
 
 
@@ -140,6 +154,7 @@ class GemmCfg(C.Structure):
         ("reps", C.c_int),
         ("seed", C.c_uint32),
         ("samples", C.c_int),
+        ("operands", C.c_int),
         ("sustain_seconds", C.c_double),
     ]
 
@@ -161,6 +176,8 @@ class GemmResult(C.Structure):
         ("c_sum64", C.c_uint64),
         ("c_xor32", C.c_uint32),
         ("verified", C.c_int),
+        ("operands", C.c_int),
+        ("max_err_over_tol", C.c_double),
     ]
 
 
@@ -182,6 +199,7 @@ SIGNATURES = {
     "b200probe_passive_health": (C.c_int, [C.c_int, _P(C.c_uint64)]),
     "b200probe_health_mask": (C.c_int, [_P(C.c_uint64)]),
     "b200probe_health_close": (None, []),
+    "b200probe_device_busy": (C.c_int, [C.c_int, _P(Busy)]),
     "b200probe_nvlink_passive": (C.c_int, [C.c_int, _P(NvlinkStatus)]),
     "b200probe_hbm_sweep": (C.c_int, [C.c_int, _P(HbmCfg), _P(HbmResult), C.c_int, _P(C.c_int)]),
     "b200probe_hbm_release": (C.c_int, [C.c_int]),
@@ -193,6 +211,7 @@ SIGNATURES = {
     "b200probe_host_alloc": (C.c_int, [C.c_uint64, _P(_vp)]),
     "b200probe_host_free": (C.c_int, [_vp]),
     "b200probe_nvlink_a2a": (C.c_int, [_P(C.c_int), C.c_int, _P(A2aCfg), _P(C.c_double), _P(A2aResult)]),
+    "b200probe_a2a_release": (C.c_int, []),
     "b200probe_enable_peer_access": (C.c_int, [_P(C.c_int), C.c_int]),
     "b200probe_a2a_window_create": (C.c_int, [C.c_int, C.c_int, C.c_uint64, _P(_vp), C.c_char_p]),
     "b200probe_a2a_window_import": (C.c_int, [C.c_int, C.c_char_p, _P(_vp)]),
@@ -201,6 +220,8 @@ SIGNATURES = {
     "b200probe_a2a_exchange": (C.c_int, [C.c_int, C.c_int, C.c_int, _P(_vp), C.c_uint64, C.c_uint32, C.c_int, C.c_int, C.c_int, _vp]),
     "b200probe_a2a_chunk_seed": (C.c_uint32, [C.c_uint32, C.c_int, C.c_int]),
     "b200probe_gemm": (C.c_int, [C.c_int, _P(GemmCfg), _P(GemmResult)]),
+    "b200probe_gemm_release": (C.c_int, [C.c_int]),
+    "b200probe_gemm_operand_bits": (C.c_uint16, [C.c_uint64, C.c_uint32, C.c_int]),
     "b200probe_gemm_launch": (C.c_int, [C.c_int, _vp, _vp, _vp, C.c_int, C.c_int, C.c_int, _vp]),
     "b200probe_gemm_fill": (C.c_int, [C.c_int, _vp, C.c_uint64, C.c_uint32, C.c_int, _vp]),
     "b200probe_pattern_word": (C.c_uint32, [C.c_uint64, C.c_uint32]),
@@ -224,7 +245,7 @@ def load() -> C.CDLL:
         fn = getattr(lib, name)  # AttributeError = ABI drift; let it propagate
         fn.restype = res
         fn.argtypes = args
-    if lib.b200probe_abi_version() != 1:
-        raise ImportError(f"libb200probe.so ABI {lib.b200probe_abi_version()} != 1")
+    if lib.b200probe_abi_version() != ABI_VERSION:
+        raise ImportError(f"libb200probe.so ABI {lib.b200probe_abi_version()} != {ABI_VERSION}")
     _lib = lib
     return lib

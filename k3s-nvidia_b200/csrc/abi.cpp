@@ -11,6 +11,7 @@
 #include <nvml.h>
 #include <pthread.h>
 #include <time.h>
+#include <unistd.h>
 
 #include <cctype>
 #include <cstdlib>
@@ -43,6 +44,8 @@ struct Nvml {
     nvmlReturn_t (*DeviceGetNvLinkState)(nvmlDevice_t, unsigned int, nvmlEnableState_t*);    // optional
     nvmlReturn_t (*DeviceGetFieldValues)(nvmlDevice_t, int, nvmlFieldValue_t*);              // optional
     nvmlReturn_t (*DeviceGetGpuFabricInfoV)(nvmlDevice_t, nvmlGpuFabricInfoV_t*);            // optional
+    nvmlReturn_t (*DeviceGetComputeRunningProcesses_v3)(nvmlDevice_t, unsigned int*, nvmlProcessInfo_t*);   // optional
+    nvmlReturn_t (*DeviceGetUtilizationRates)(nvmlDevice_t, nvmlUtilization_t*);                          // optional
 };
 
 struct Device {
@@ -65,6 +68,7 @@ struct State {
     int cuda_count = 0;
     std::vector<std::string> cuda_uuid;
     std::vector<b200::DevProps> cuda_props;
+    std::vector<char> cuda_touched;       // a probe of this process has run on the ordinal: the process owns a context there
 };
 State g;
 
@@ -161,6 +165,7 @@ int cuda_init_locked() {
     g.cuda_count = n;
     g.cuda_uuid.resize(n);
     g.cuda_props.resize(n);
+    g.cuda_touched.assign(n, 0);
     for (int i = 0; i < n; ++i) {
         cudaDeviceProp p;
         e = cudaGetDeviceProperties(&p, i);
@@ -312,6 +317,7 @@ int device_props(int ordinal, DevProps* out) {
     if (rc) return rc;
     if (ordinal < 0 || ordinal >= g.cuda_count) { set_error("CUDA ordinal %d out of range", ordinal); return B200PROBE_ERANGE; }
     *out = g.cuda_props[ordinal];
+    g.cuda_touched[ordinal] = 1;          // every probe entry point passes here before it sets the device
     if (out->cc_major != 10) {
         set_error("CUDA device %d is sm_%d%d; the probe kernels are sm_100a-only", ordinal, out->cc_major, out->cc_minor);
         return B200PROBE_EARCH;
@@ -349,6 +355,8 @@ int b200probe_init(const char* path) {
     sym(lib, "nvmlDeviceGetNvLinkState", n.DeviceGetNvLinkState, false);
     sym(lib, "nvmlDeviceGetFieldValues", n.DeviceGetFieldValues, false);
     sym(lib, "nvmlDeviceGetGpuFabricInfoV", n.DeviceGetGpuFabricInfoV, false);
+    sym(lib, "nvmlDeviceGetComputeRunningProcesses_v3", n.DeviceGetComputeRunningProcesses_v3, false);
+    sym(lib, "nvmlDeviceGetUtilizationRates", n.DeviceGetUtilizationRates, false);
     if (!ok) { dlclose(lib); return B200PROBE_ENVML; }
     nvmlReturn_t r = n.Init_v2();
     if (r != NVML_SUCCESS) { b200::set_error("nvmlInit_v2: %s", n.ErrorString(r)); dlclose(lib); return nvml_rc(r); }
@@ -530,6 +538,41 @@ int b200probe_nvlink_passive(int idx, b200probe_nvlink_status_t* out) {
             out->counters_ok = ok;
         }
     }
+    return 0;
+}
+
+// Is somebody else using this GPU?  The active probes measure against idle-box figures and take SMs, HBM bandwidth and
+// memory from whatever runs beside them, so the host asks before every round and skips (does not fail) a busy device.
+int b200probe_device_busy(int idx, b200probe_busy_t* out) {
+    if (!out) return B200PROBE_EINVAL;
+    Lock l;
+    if (!g.inited) return B200PROBE_ENOTINIT;
+    if (idx < 0 || idx >= (int)g.devs.size()) return B200PROBE_ERANGE;
+    memset(out, 0, sizeof(*out));
+    out->compute_procs = out->util_gpu_pct = out->util_mem_pct = -1;
+    nvmlDevice_t h = g.devs[idx].h;
+    if (g.nvml.DeviceGetComputeRunningProcesses_v3) {
+        std::vector<nvmlProcessInfo_t> procs(64);
+        unsigned count = (unsigned)procs.size();
+        nvmlReturn_t r = g.nvml.DeviceGetComputeRunningProcesses_v3(h, &count, procs.data());
+        if (r == NVML_ERROR_INSUFFICIENT_SIZE) { procs.resize(count + 16); count = (unsigned)procs.size(); r = g.nvml.DeviceGetComputeRunningProcesses_v3(h, &count, procs.data()); }
+        if (r == NVML_SUCCESS) {
+            const unsigned self = (unsigned)getpid();
+            int others = 0;
+            bool saw_self = false;
+            for (unsigned i = 0; i < count; ++i) { if (procs[i].pid == self) saw_self = true; else ++others; }
+            // NVML reports pids of the HOST namespace: inside a container our own context shows up under a pid we cannot
+            // recognise.  If this process has run a probe on the device and did not find itself, one of the entries is us.
+            const int ord = g.devs[idx].info.cuda_ordinal;
+            if (!saw_self && others > 0 && ord >= 0 && ord < (int)g.cuda_touched.size() && g.cuda_touched[ord]) --others;
+            out->compute_procs = others;
+        }
+    }
+    nvmlUtilization_t u;
+    if (g.nvml.DeviceGetUtilizationRates && g.nvml.DeviceGetUtilizationRates(h, &u) == NVML_SUCCESS) { out->util_gpu_pct = (int)u.gpu; out->util_mem_pct = (int)u.memory; }
+    nvmlMemory_t mem;
+    if (g.nvml.DeviceGetMemoryInfo(h, &mem) == NVML_SUCCESS) out->mem_used = mem.used;
+    out->busy = (out->compute_procs > 0 || out->util_gpu_pct >= B200PROBE_BUSY_UTIL_PCT) ? 1 : 0;
     return 0;
 }
 

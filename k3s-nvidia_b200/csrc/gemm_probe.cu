@@ -6,18 +6,24 @@
 //   warp 0   TMA producer   cp.async.bulk.tensor (SASS UTMALDG) 128B-swizzled A/B tiles -> smem ring
 //   warp 1   MMA issuer     one lane issues tcgen05.mma (SASS UTCHMMA) M=128 N=256 K=16, smem x smem -> TMEM
 //   warp 2   TMEM allocator tcgen05.alloc 512 columns = two 128x256 fp32 accumulators (double buffer)
-//   warps 4-7 epilogue      tcgen05.ld (LDTM) 32 lanes x 32 columns -> cvt bf16 -> global
+//   warps 4-7 epilogue      tcgen05.ld (LDTM) 32 lanes x 32 columns, two register sets in flight -> cvt bf16 ->
+//                           128B-swizzled shared-memory staging -> cp.async.bulk.tensor store (SASS UTMASTG), 64 columns at a time
 // Pipelines: smem full/empty mbarriers (TMA <-> MMA), TMEM full/empty mbarriers (MMA <-> epilogue),
 // so the epilogue of tile i overlaps the MMAs of tile i+1.
 //
 // Roofline: tensor bound.  Algorithmic work per launch: 2*M*N*K flop.
-// Operands come from a closed-form generator whose values (k/128, k integer) make every partial
-// sum exactly representable in fp32, so C is bit-exact against the fp64 oracle after one bf16 RNE.
+// Two operand classes (cfg.operands):
+//   0 EXACT    closed-form values k/128 (k integer): every partial sum is exactly representable in fp32, so C is
+//              bit-exact against the fp64 oracle after one bf16 RNE (the probe's default: a health verdict with no tolerance)
+//   1 UNIFORM  SURVEY.md §8d's input class: bf16 U(-1,1) from Philox4x32-10, key (seed, 0); sampled outputs against fp64
+//              dot products within |err| <= 2^-8 |ref| + 2^-10 sqrt(K) (final bf16 rounding + fp32 accumulation allowance)
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
+#include <pthread.h>
 
 #include <algorithm>
+#include <cmath>
 #include <cstdlib>
 #include <vector>
 
@@ -33,7 +39,10 @@ constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
 constexpr int NUM_THREADS = 256;
 constexpr int TMEM_COLS = 512;
 constexpr int GROUP_M = 16;                         // rasterisation: 16 m-tiles per band (L2 reuse)
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+constexpr int EPI_UNIT_COLS = 64;                   // one TMA store = 32 rows x 64 bf16 columns = 32 x 128 B (one swizzle atom wide)
+constexpr int EPI_BUF_BYTES = 32 * EPI_UNIT_COLS * 2;                 // 4 KiB
+constexpr int EPI_BYTES = 4 /*warps*/ * 2 /*buffers*/ * EPI_BUF_BYTES;    // 32 KiB
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + 1024 /*align*/ + 256 /*barriers*/;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
@@ -90,6 +99,63 @@ __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&v)[32])
         : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src_smem, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"((uint64_t)map), "r"(src_smem), "r"(c0), "r"(c1)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_commit_group() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// 32 fp32 accumulator columns of this lane's row -> 32 bf16 -> the 64-byte half `half` of the row's 128-byte line in the
+// staging buffer, in the SWIZZLE_128B layout the C tensor map expects: 16-byte chunk j of row r sits at chunk j ^ (r & 7).
+// (Rows are 128 B apart, so the 8 lanes of a store phase hit 8 different chunk columns: conflict-free.)
+__device__ __forceinline__ void pack_half_row(const uint32_t (&v)[32], uint8_t* row, int half, int lane) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        uint32_t pk[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            __nv_bfloat162 h = __floats2bfloat162_rn(__uint_as_float(v[8 * j + 2 * i]), __uint_as_float(v[8 * j + 2 * i + 1]));
+            pk[i] = *reinterpret_cast<uint32_t*>(&h);
+        }
+        *reinterpret_cast<uint4*>(row + (((half * 4 + j) ^ (lane & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+    }
+}
+
+// Epilogue of one 32-row x 256-column slice (this warp's TMEM lane quadrant of one accumulator).  tcgen05.ld of the next 32
+// columns is in flight while the previous 32 are converted (two register sets); 64 columns at a time leave through a
+// swizzled staging buffer and ONE tensor store (full 128-byte lines instead of 16-byte pieces of 32 different lines);
+// two staging buffers per warp, so a store drains while the next unit is packed.  `release` hands the accumulator back
+// to the MMA issuer as soon as the last tcgen05.ld has landed, before the stores finish.
+template <class Release>
+__device__ __forceinline__ void epilogue_slice(uint32_t taddr, uint8_t* stage, uint32_t& ubuf, const CUtensorMap* tmc, int row0, int col0, int lane,
+                                               Release release) {
+    uint32_t va[32], vb[32];
+    tmem_ld_32x32(taddr, va);
+    tmem_ld_wait();
+#pragma unroll
+    for (int u = 0; u < BN / EPI_UNIT_COLS; ++u) {
+        tmem_ld_32x32(taddr + u * EPI_UNIT_COLS + 32, vb);          // in flight during the conversion of va
+        if (lane == 0) bulk_wait_read1();                           // the store that read this buffer two units ago is done with it
+        __syncwarp();
+        uint8_t* buf = stage + ubuf * EPI_BUF_BYTES;
+        pack_half_row(va, buf + lane * 128, 0, lane);
+        tmem_ld_wait();
+        if (u + 1 < BN / EPI_UNIT_COLS) tmem_ld_32x32(taddr + (u + 1) * EPI_UNIT_COLS, va);
+        else release();                                             // every column of this accumulator slice is in registers
+        pack_half_row(vb, buf + lane * 128, 1, lane);
+        fence_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+            tma_store_2d(tmc, smem_u32(buf), col0 + u * EPI_UNIT_COLS, row0);
+            bulk_commit_group();
+        }
+        ubuf ^= 1;
+        if (u + 1 < BN / EPI_UNIT_COLS) tmem_ld_wait();
+    }
+}
 
 // K-major operand tile [rows][64 bf16] written by TMA with SWIZZLE_128B: 8-row x 128-byte atoms,
 // 1024 bytes apart (SBO); LBO is unused for swizzled K-major layouts; descriptor version 1 (sm_100).
@@ -115,13 +181,14 @@ __device__ __forceinline__ TileCoord tile_coord(int t, int num_m, int num_n) {
 }
 
 __global__ void __launch_bounds__(NUM_THREADS, 1)
-gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, __nv_bfloat16* __restrict__ C,
+gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, const __grid_constant__ CUtensorMap tma_c,
                     int M, int N, int K) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     uint8_t* smem_a = smem;
     uint8_t* smem_b = smem + STAGES * A_STAGE_BYTES;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+    uint8_t* smem_epi = smem + STAGES * STAGE_BYTES;            // 4 warps x 2 x 4 KiB, 1024-aligned (swizzle atoms)
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_epi + EPI_BYTES);
     uint64_t* full = bars;                  // [STAGES]
     uint64_t* empty = bars + STAGES;        // [STAGES]
     uint64_t* tfull = bars + 2 * STAGES;    // [2]
@@ -134,6 +201,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tma_a) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tma_b) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tma_c) : "memory");
     }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < STAGES; ++s) { mbar_init(smem_u32(&full[s]), 1); mbar_init(smem_u32(&empty[s]), 1); }
@@ -190,34 +258,21 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
         }
     } else if (warp >= 4) {                                // ===== epilogue =====
         const int q = warp - 4;                            // == warp % 4: the TMEM lane quadrant this warp may read
-        uint32_t it = 0;
+        uint32_t it = 0, ubuf = 0;
         for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
             const TileCoord tc = tile_coord(t, num_m, num_n);
             const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
             mbar_wait(smem_u32(&tfull[acc]), acc_phase);
             tc_fence_after();
-            const int row = tc.m0 + q * 32 + lane;
-            __nv_bfloat16* crow = C + (size_t)row * N + tc.n0;
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN;
-#pragma unroll 1
-            for (int c = 0; c < BN / 32; ++c) {
-                uint32_t v[32];
-                tmem_ld_32x32(taddr + c * 32, v);
-                tmem_ld_wait();
-                uint32_t pk[16];
-#pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                    __nv_bfloat162 h = __floats2bfloat162_rn(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]));
-                    pk[j] = *reinterpret_cast<uint32_t*>(&h);
-                }
-                uint4* dst = reinterpret_cast<uint4*>(crow + c * 32);
-#pragma unroll
-                for (int j = 0; j < 4; ++j) dst[j] = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
-            }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(smem_u32(&tempty[acc]));
+            const uint32_t tempty_bar = smem_u32(&tempty[acc]);
+            epilogue_slice(taddr, smem_epi + q * 2 * EPI_BUF_BYTES, ubuf, &tma_c, tc.m0 + q * 32, tc.n0, lane, [&]() {
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(tempty_bar);
+            });
         }
+        if (lane == 0) bulk_wait_all0();                   // the staging buffers are read by the TMA unit until then
     }
     tc_fence_before();
     __syncthreads();
@@ -260,7 +315,8 @@ constexpr int STAGES2 = 6;
 constexpr int A2_STAGE_BYTES = BM * BK * 2;             // this CTA's 128 rows of the 256-row A tile
 constexpr int B2_STAGE_BYTES = (BN / 2) * BK * 2;       // this CTA's 128 of the 256 B rows
 constexpr int STAGE2_BYTES = A2_STAGE_BYTES + B2_STAGE_BYTES;     // 32 KiB per CTA per stage
-constexpr int SMEM2_BYTES = STAGES2 * STAGE2_BYTES + 1024 + 256;
+constexpr int SMEM2_BYTES = STAGES2 * STAGE2_BYTES + EPI_BYTES + 1024 + 256;
+static_assert(SMEM2_BYTES <= 232448 && SMEM_BYTES <= 232448, "227 KiB of shared memory per CTA");
 constexpr uint32_t kIdesc2 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((2 * BM) >> 4) << 24);   // M = 256
 
 __device__ __forceinline__ TileCoord tile_coord2(int t, int num_m, int num_n) {     // tiles of (2*BM) x BN
@@ -276,13 +332,14 @@ __device__ __forceinline__ TileCoord tile_coord2(int t, int num_m, int num_n) { 
 // 128 A rows and 128 of the 256 B rows (half the shared-memory fill and L2 traffic per flop of the
 // 1-CTA kernel), holds its 128 accumulator rows in its own TMEM and runs its own epilogue.
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
-gemm_bf16_tn_2cta_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, __nv_bfloat16* __restrict__ C,
+gemm_bf16_tn_2cta_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, const __grid_constant__ CUtensorMap tma_c,
                          int M, int N, int K) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     uint8_t* smem_a = smem;
     uint8_t* smem_b = smem + STAGES2 * A2_STAGE_BYTES;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES2 * STAGE2_BYTES);
+    uint8_t* smem_epi = smem + STAGES2 * STAGE2_BYTES;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_epi + EPI_BYTES);
     uint64_t* full = bars;                   // [STAGES2]  used in the leader only
     uint64_t* empty = bars + STAGES2;        // [STAGES2]  one per CTA, signalled by multicast commit
     uint64_t* tfull = bars + 2 * STAGES2;    // [2]        one per CTA, signalled by multicast commit
@@ -298,6 +355,7 @@ gemm_bf16_tn_2cta_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tma_a) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tma_b) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tma_c) : "memory");
     }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < STAGES2; ++s) { mbar_init(smem_u32(&full[s]), 1); mbar_init(smem_u32(&empty[s]), 1); }
@@ -353,34 +411,21 @@ gemm_bf16_tn_2cta_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid
         }
     } else if (warp >= 4) {                                // ===== epilogue (both CTAs, own 128 rows) =====
         const int q = warp - 4;
-        uint32_t it = 0;
+        uint32_t it = 0, ubuf = 0;
         for (int t = pair; t < num_tiles; t += num_pairs, ++it) {
             const TileCoord tc = tile_coord2(t, num_m, num_n);
             const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
             mbar_wait(smem_u32(&tfull[acc]), acc_phase);
             tc_fence_after();
-            const int row = tc.m0 + (int)cta_rank * BM + q * 32 + lane;
-            __nv_bfloat16* crow = C + (size_t)row * N + tc.n0;
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN;
-#pragma unroll 1
-            for (int c = 0; c < BN / 32; ++c) {
-                uint32_t v[32];
-                tmem_ld_32x32(taddr + c * 32, v);
-                tmem_ld_wait();
-                uint32_t pk[16];
-#pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                    __nv_bfloat162 h = __floats2bfloat162_rn(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]));
-                    pk[j] = *reinterpret_cast<uint32_t*>(&h);
-                }
-                uint4* dst = reinterpret_cast<uint4*>(crow + c * 32);
-#pragma unroll
-                for (int j = 0; j < 4; ++j) dst[j] = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
-            }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive_leader(smem_u32(&tempty[acc]));
+            const uint32_t tempty_bar = smem_u32(&tempty[acc]);
+            epilogue_slice(taddr, smem_epi + q * 2 * EPI_BUF_BYTES, ubuf, &tma_c, tc.m0 + (int)cta_rank * BM + q * 32, tc.n0, lane, [&]() {
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive_leader(tempty_bar);
+            });
         }
+        if (lane == 0) bulk_wait_all0();
     }
     tc_fence_before();
     cluster_sync_all();            // the peer's MMAs read this CTA's shared memory: nobody leaves early
@@ -390,10 +435,28 @@ gemm_bf16_tn_2cta_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid
     }
 }
 
+// `which`: bit 0 = matrix (0 A, 1 B), bit 1 = operand class (0 EXACT k/128, 1 UNIFORM Philox U(-1,1))
 __global__ void gemm_fill_kernel(uint16_t* dst, uint64_t elems, uint32_t seed, int which) {
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-    for (; i < elems; i += stride) dst[i] = b200_gemm_elem_bits(i, seed, which);
+    if (which & 2) {
+        // one Philox block = 4 consecutive elements = one 8-byte store (dst is 16-byte aligned, elems a multiple of 4 up to the tail)
+        const uint64_t nblk = elems >> 2;
+        for (uint64_t b = i; b < nblk; b += stride) {
+            uint32_t r[4];
+            b200_philox4x32_10((uint32_t)b, (uint32_t)(b >> 32), (uint32_t)(which & 1), 0u, seed, 0u, r);
+            uint16_t h[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const uint32_t u = __float_as_uint((float)(r[j] >> 8) * (1.0f / 8388608.0f) - 1.0f);
+                h[j] = (uint16_t)((u + 0x7fffu + ((u >> 16) & 1u)) >> 16);
+            }
+            *reinterpret_cast<uint2*>(dst + 4 * b) = make_uint2((uint32_t)h[0] | ((uint32_t)h[1] << 16), (uint32_t)h[2] | ((uint32_t)h[3] << 16));
+        }
+        for (uint64_t e = (nblk << 2) + i; e < elems; e += stride) dst[e] = b200_gemm_uniform_bits(e, seed, which & 1);
+    } else {
+        for (; i < elems; i += stride) dst[i] = b200_gemm_elem_bits(i, seed, which);
+    }
 }
 
 __global__ void gather_kernel(const uint16_t* c, const uint64_t* idx, uint16_t* out, int n) {
@@ -421,13 +484,13 @@ int get_encode(EncodeTiledFn* fn) {
     return 0;
 }
 
-// [rows][k] bf16 row-major -> box {64 (k), box_rows}, 128B swizzle
-int make_map(CUtensorMap* map, const void* base, int rows, int k, int box_rows) {
+// [rows][inner] bf16 row-major -> box {64 (inner), box_rows}, 128B swizzle.  Operands: inner = K; C: inner = N.
+int make_map(CUtensorMap* map, const void* base, int rows, int inner, int box_rows) {
     EncodeTiledFn enc = nullptr;
     int rc = get_encode(&enc);
     if (rc) return rc;
-    cuuint64_t dims[2] = {(cuuint64_t)k, (cuuint64_t)rows};
-    cuuint64_t strides[1] = {(cuuint64_t)k * 2};
+    cuuint64_t dims[2] = {(cuuint64_t)inner, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)inner * 2};
     cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
@@ -435,6 +498,7 @@ int make_map(CUtensorMap* map, const void* base, int rows, int k, int box_rows) 
     if (r != CUDA_SUCCESS) { b200::set_error("cuTensorMapEncodeTiled failed: CUresult %d", (int)r); return B200PROBE_CUDA_BASE + 1; }
     return 0;
 }
+static_assert(EPI_UNIT_COLS == BK, "the C map reuses the operands' 64-element (128-byte) box width");
 
 int check_shape(int m, int n, int k) {
     if (m <= 0 || n <= 0 || k <= 0 || m % BM || n % BN || k % BK) {
@@ -463,22 +527,74 @@ uint16_t float_to_bf16_rne(float f) {
     return (uint16_t)((u + r) >> 16);
 }
 
-struct GemmBufs {
+// Per-device resident arena (like hbm_sweep.cu's): operands stay filled between calls with the same shape, seed and
+// operand class — the daemon probes periodically, and 384 MiB of cudaMalloc + two fills cost more than the ten timed GEMMs.
+struct GemmArena {
+    pthread_mutex_t mu = PTHREAD_MUTEX_INITIALIZER;
     void *a = nullptr, *b = nullptr, *c = nullptr, *idx = nullptr, *out = nullptr;
     unsigned long long* partials = nullptr;
     cudaStream_t stream = nullptr;
     cudaEvent_t e0 = nullptr, e1 = nullptr;
-    ~GemmBufs() {
-        if (a) cudaFree(a);
-        if (b) cudaFree(b);
-        if (c) cudaFree(c);
-        if (idx) cudaFree(idx);
-        if (out) cudaFree(out);
-        if (partials) cudaFree(partials);
-        if (e0) cudaEventDestroy(e0);
-        if (e1) cudaEventDestroy(e1);
-        if (stream) cudaStreamDestroy(stream);
+    int m = 0, n = 0, k = 0, operands = -1, samples_cap = 0;
+    uint32_t seed = 0;
+    bool filled = false;
+};
+GemmArena g_gemm[B200PROBE_MAX_DEVICES];
+
+void gemm_arena_free(GemmArena& g) {
+    if (g.a) cudaFree(g.a);
+    if (g.b) cudaFree(g.b);
+    if (g.c) cudaFree(g.c);
+    if (g.idx) cudaFree(g.idx);
+    if (g.out) cudaFree(g.out);
+    if (g.partials) cudaFree(g.partials);
+    if (g.e0) cudaEventDestroy(g.e0);
+    if (g.e1) cudaEventDestroy(g.e1);
+    if (g.stream) cudaStreamDestroy(g.stream);
+    g.a = g.b = g.c = g.idx = g.out = nullptr;
+    g.partials = nullptr; g.e0 = g.e1 = nullptr; g.stream = nullptr;
+    g.m = g.n = g.k = 0; g.operands = -1; g.samples_cap = 0; g.filled = false;
+}
+
+#define B200_ALLOC_TRY(expr)                                                                                  \
+    do {                                                                                                      \
+        cudaError_t e__ = (expr);                                                                             \
+        if (e__ == cudaErrorMemoryAllocation) { cudaGetLastError(); b200::set_error("%s: out of device memory", #expr); return B200PROBE_ENOMEM; } \
+        if (e__ != cudaSuccess) { b200::set_error("%s:%d %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(e__)); return b200::cuda_rc((int)e__); } \
+    } while (0)
+
+int gemm_arena_reserve(GemmArena& g, int M, int N, int K, int samples) {
+    if (!g.stream) {
+        B200_CUDA_TRY(cudaStreamCreateWithFlags(&g.stream, cudaStreamNonBlocking));
+        B200_CUDA_TRY(cudaEventCreate(&g.e0));
+        B200_CUDA_TRY(cudaEventCreate(&g.e1));
+        B200_ALLOC_TRY(cudaMalloc(&g.partials, 32));
     }
+    if (M != g.m || N != g.n || K != g.k) {
+        if (g.a) cudaFree(g.a);
+        if (g.b) cudaFree(g.b);
+        if (g.c) cudaFree(g.c);
+        g.a = g.b = g.c = nullptr; g.m = g.n = g.k = 0; g.filled = false;
+        B200_ALLOC_TRY(cudaMalloc(&g.a, (size_t)M * K * 2));
+        B200_ALLOC_TRY(cudaMalloc(&g.b, (size_t)N * K * 2));
+        B200_ALLOC_TRY(cudaMalloc(&g.c, (size_t)M * N * 2));
+        g.m = M; g.n = N; g.k = K;
+    }
+    if (samples > g.samples_cap) {
+        if (g.idx) cudaFree(g.idx);
+        if (g.out) cudaFree(g.out);
+        g.idx = g.out = nullptr; g.samples_cap = 0;
+        B200_ALLOC_TRY(cudaMalloc(&g.idx, (size_t)samples * 8));
+        B200_ALLOC_TRY(cudaMalloc(&g.out, (size_t)samples * 2));
+        g.samples_cap = samples;
+    }
+    return 0;
+}
+
+struct GemmLock {
+    GemmArena& g;
+    explicit GemmLock(GemmArena& x) : g(x) { pthread_mutex_lock(&g.mu); }
+    ~GemmLock() { pthread_mutex_unlock(&g.mu); }
 };
 
 }  // namespace
@@ -489,11 +605,15 @@ int b200probe_gemm_fill(int ordinal, void* dst, uint64_t elems, uint32_t seed, i
     b200::DevProps props;
     int rc = b200::device_props(ordinal, &props);
     if (rc) return rc;
-    if (!dst || (which != 0 && which != 1)) return B200PROBE_EINVAL;
+    if (!dst || which < 0 || which > 3 || (((uintptr_t)dst) & 15)) return B200PROBE_EINVAL;
     B200_CUDA_TRY(cudaSetDevice(ordinal));
     if (elems) gemm_fill_kernel<<<props.sms * 8, 256, 0, (cudaStream_t)stream>>>((uint16_t*)dst, elems, seed, which);
     B200_CUDA_TRY(cudaGetLastError());
     return 0;
+}
+
+uint16_t b200probe_gemm_operand_bits(uint64_t elem, uint32_t seed, int which) {
+    return (which & 2) ? b200_gemm_uniform_bits(elem, seed, which & 1) : b200_gemm_elem_bits(elem, seed, which & 1);
 }
 
 // kernel variant: 2 = CTA-pair kernel (default when M is a multiple of 256), 1 = single-CTA kernel.
@@ -517,65 +637,49 @@ int b200probe_gemm_launch(int ordinal, const void* a, const void* b, void* c, in
     if (!a || !b || !c || (((uintptr_t)a | (uintptr_t)b | (uintptr_t)c) & 15)) { b200::set_error("gemm: operands must be 16-byte aligned device pointers"); return B200PROBE_EINVAL; }
     B200_CUDA_TRY(cudaSetDevice(ordinal));
     const int variant = gemm_variant_for(m);
-    CUtensorMap ma, mb;
+    CUtensorMap ma, mb, mc;
     rc = make_map(&ma, a, m, k, BM);
     if (rc) return rc;
     rc = make_map(&mb, b, n, k, variant == 2 ? BN / 2 : BN);
+    if (rc) return rc;
+    rc = make_map(&mc, c, m, n, 32);            // the epilogue stores 32 rows x 64 columns per tensor store
     if (rc) return rc;
     if (variant == 2) {
         B200_CUDA_TRY(cudaFuncSetAttribute(gemm_bf16_tn_2cta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM2_BYTES));
         const int tiles = (m / (2 * BM)) * (n / BN);
         const int pairs = std::min(tiles, props.sms / 2);
-        gemm_bf16_tn_2cta_kernel<<<2 * pairs, NUM_THREADS, SMEM2_BYTES, (cudaStream_t)stream>>>(ma, mb, (__nv_bfloat16*)c, m, n, k);
+        gemm_bf16_tn_2cta_kernel<<<2 * pairs, NUM_THREADS, SMEM2_BYTES, (cudaStream_t)stream>>>(ma, mb, mc, m, n, k);
     } else {
         B200_CUDA_TRY(cudaFuncSetAttribute(gemm_bf16_tn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
         const int tiles = (m / BM) * (n / BN);
         const int grid = std::min(tiles, props.sms);
-        gemm_bf16_tn_kernel<<<grid, NUM_THREADS, SMEM_BYTES, (cudaStream_t)stream>>>(ma, mb, (__nv_bfloat16*)c, m, n, k);
+        gemm_bf16_tn_kernel<<<grid, NUM_THREADS, SMEM_BYTES, (cudaStream_t)stream>>>(ma, mb, mc, m, n, k);
     }
     B200_CUDA_TRY(cudaGetLastError());
     return 0;
 }
 
-int b200probe_gemm(int idx, const b200probe_gemm_cfg_t* cfg_in, b200probe_gemm_result_t* out) {
-    if (!out) return B200PROBE_EINVAL;
-    int ordinal = -1;
-    int rc = b200::cuda_ordinal_of(idx, &ordinal);
-    if (rc) return rc;
-    b200::DevProps props;
-    rc = b200::device_props(ordinal, &props);
-    if (rc) return rc;
-    b200probe_gemm_cfg_t cfg;
-    memset(&cfg, 0, sizeof(cfg));
-    if (cfg_in) cfg = *cfg_in;
-    if (!cfg.m) cfg.m = 8192;
-    if (!cfg.n) cfg.n = 8192;
-    if (!cfg.k) cfg.k = 8192;
-    if (!cfg.warmup && !cfg.reps) { cfg.warmup = 3; cfg.reps = 10; }
-    if (cfg.reps < 1) cfg.reps = 1;
-    if (!cfg.seed) cfg.seed = 0xB200u;
-    if (!cfg.samples) cfg.samples = 1024;
-    rc = check_shape(cfg.m, cfg.n, cfg.k);
-    if (rc) return rc;
-    const int M = cfg.m, N = cfg.n, K = cfg.k;
-    memset(out, 0, sizeof(*out));
-    out->m = M; out->n = N; out->k = K;
-    out->verified = -1;
+int b200probe_gemm_release(int ordinal) {
+    if (ordinal < 0 || ordinal >= B200PROBE_MAX_DEVICES) return B200PROBE_ERANGE;
+    GemmArena& g = g_gemm[ordinal];
+    GemmLock lock(g);
+    if (g.stream) { cudaSetDevice(ordinal); gemm_arena_free(g); }
+    return 0;
+}
 
-    B200_CUDA_TRY(cudaSetDevice(ordinal));
-    GemmBufs g;
-    B200_CUDA_TRY(cudaStreamCreateWithFlags(&g.stream, cudaStreamNonBlocking));
-    B200_CUDA_TRY(cudaEventCreate(&g.e0));
-    B200_CUDA_TRY(cudaEventCreate(&g.e1));
-    B200_CUDA_TRY(cudaMalloc(&g.a, (size_t)M * K * 2));
-    B200_CUDA_TRY(cudaMalloc(&g.b, (size_t)N * K * 2));
-    B200_CUDA_TRY(cudaMalloc(&g.c, (size_t)M * N * 2));
-    B200_CUDA_TRY(cudaMalloc(&g.partials, 16));
-    B200_CUDA_TRY(cudaMemsetAsync(g.c, 0xFF, (size_t)M * N * 2, g.stream));
-    rc = b200probe_gemm_fill(ordinal, g.a, (uint64_t)M * K, cfg.seed, 0, g.stream);
+static int gemm_locked(int ordinal, GemmArena& g, const b200probe_gemm_cfg_t& cfg, b200probe_gemm_result_t* out) {
+    const int M = cfg.m, N = cfg.n, K = cfg.k, S = cfg.samples;
+    const int cls = cfg.operands;
+    int rc = gemm_arena_reserve(g, M, N, K, S);
     if (rc) return rc;
-    rc = b200probe_gemm_fill(ordinal, g.b, (uint64_t)N * K, cfg.seed, 1, g.stream);
-    if (rc) return rc;
+    if (!g.filled || g.seed != cfg.seed || g.operands != cls) {
+        rc = b200probe_gemm_fill(ordinal, g.a, (uint64_t)M * K, cfg.seed, 0 | (cls << 1), g.stream);
+        if (rc) return rc;
+        rc = b200probe_gemm_fill(ordinal, g.b, (uint64_t)N * K, cfg.seed, 1 | (cls << 1), g.stream);
+        if (rc) return rc;
+        g.filled = true; g.seed = cfg.seed; g.operands = cls;
+    }
+    B200_CUDA_TRY(cudaMemsetAsync(g.c, 0xFF, (size_t)M * N * 2, g.stream));      // poison: a tile the kernel skipped cannot pass the check
 
     std::vector<float> ms((size_t)cfg.reps);
     for (int it = -cfg.warmup; it < cfg.reps; ++it) {
@@ -620,7 +724,6 @@ int b200probe_gemm(int idx, const b200probe_gemm_cfg_t* cfg_in, b200probe_gemm_r
     if (rc) return rc;
     unsigned long long h[2];
     B200_CUDA_TRY(cudaMemcpyAsync(h, g.partials, 16, cudaMemcpyDeviceToHost, g.stream));
-    const int S = cfg.samples;
     std::vector<uint64_t> idxs((size_t)S);
     for (int i = 0; i < S; ++i) {
         // corners and tile seams first, then a hash-scattered set
@@ -630,8 +733,6 @@ int b200probe_gemm(int idx, const b200probe_gemm_cfg_t* cfg_in, b200probe_gemm_r
         else { r = b200_mix32(cfg.seed ^ (0x9E37u * i)) % (uint32_t)M; c = b200_mix32(cfg.seed + 77u * i + 1) % (uint32_t)N; }
         idxs[i] = (uint64_t)r * N + c;
     }
-    B200_CUDA_TRY(cudaMalloc(&g.idx, (size_t)S * 8));
-    B200_CUDA_TRY(cudaMalloc(&g.out, (size_t)S * 2));
     B200_CUDA_TRY(cudaMemcpyAsync(g.idx, idxs.data(), (size_t)S * 8, cudaMemcpyHostToDevice, g.stream));
     gather_kernel<<<(S + 255) / 256, 256, 0, g.stream>>>((const uint16_t*)g.c, (const uint64_t*)g.idx, (uint16_t*)g.out, S);
     B200_CUDA_TRY(cudaGetLastError());
@@ -641,27 +742,69 @@ int b200probe_gemm(int idx, const b200probe_gemm_cfg_t* cfg_in, b200probe_gemm_r
     out->c_sum64 = h[0];
     out->c_xor32 = (uint32_t)h[1];
     int bad = 0;
-    double max_abs = 0, max_rel = 0;
+    double max_abs = 0, max_rel = 0, max_over_tol = 0;
+    const double acc_allow = ldexp(sqrt((double)K), -10);      // UNIFORM: fp32 accumulation allowance, 2^-10 sqrt(K)
     for (int i = 0; i < S; ++i) {
         const uint64_t r = idxs[i] / N, c = idxs[i] % N;
         double acc = 0;
         for (int k = 0; k < K; ++k)
-            acc += (double)bf16_bits_to_float(b200_gemm_elem_bits(r * K + k, cfg.seed, 0)) * (double)bf16_bits_to_float(b200_gemm_elem_bits(c * K + k, cfg.seed, 1));
-        const uint16_t want = float_to_bf16_rne((float)acc);
+            acc += (double)bf16_bits_to_float(b200probe_gemm_operand_bits(r * K + k, cfg.seed, 0 | (cls << 1))) *
+                   (double)bf16_bits_to_float(b200probe_gemm_operand_bits(c * K + k, cfg.seed, 1 | (cls << 1)));
         const double gotf = bf16_bits_to_float(got[i]);
         const double err = fabs(gotf - acc);
         max_abs = std::max(max_abs, err);
         if (acc != 0) max_rel = std::max(max_rel, err / fabs(acc));
-        if (got[i] != want) ++bad;      // bit-exact bar: operands make every partial sum exact in fp32
+        if (cls == B200PROBE_GEMM_OPERANDS_EXACT) {
+            if (got[i] != float_to_bf16_rne((float)acc)) ++bad;      // bit-exact bar: operands make every partial sum exact in fp32
+        } else {
+            const double tol = ldexp(fabs(acc), -8) + acc_allow;      // half a bf16 ulp of the result + the accumulation allowance
+            max_over_tol = std::max(max_over_tol, err / tol);
+            if (!(err <= tol)) ++bad;                                 // also catches NaN
+        }
     }
     out->samples = S; out->bad = bad;
-    out->max_abs_err = max_abs; out->max_rel_err = max_rel;
+    out->max_abs_err = max_abs; out->max_rel_err = max_rel; out->max_err_over_tol = max_over_tol;
     out->verified = bad == 0 ? 1 : 0;
     if (bad) {
-        b200::set_error("gemm: %d of %d sampled outputs differ from the fp64 contraction rounded to bf16 (max abs err %g)", bad, S, max_abs);
+        b200::set_error("gemm: %d of %d sampled outputs %s (max abs err %g)", bad, S,
+                        cls == B200PROBE_GEMM_OPERANDS_EXACT ? "differ from the fp64 contraction rounded to bf16" : "are outside 2^-8|ref| + 2^-10 sqrt(K) of the fp64 contraction", max_abs);
         return B200PROBE_EMISMATCH;
     }
     return 0;
+}
+
+int b200probe_gemm(int idx, const b200probe_gemm_cfg_t* cfg_in, b200probe_gemm_result_t* out) {
+    if (!out) return B200PROBE_EINVAL;
+    int ordinal = -1;
+    int rc = b200::cuda_ordinal_of(idx, &ordinal);
+    if (rc) return rc;
+    b200::DevProps props;
+    rc = b200::device_props(ordinal, &props);
+    if (rc) return rc;
+    b200probe_gemm_cfg_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    if (cfg_in) cfg = *cfg_in;
+    if (!cfg.m) cfg.m = 8192;
+    if (!cfg.n) cfg.n = 8192;
+    if (!cfg.k) cfg.k = 8192;
+    if (!cfg.warmup && !cfg.reps) { cfg.warmup = 3; cfg.reps = 10; }
+    if (cfg.reps < 1) cfg.reps = 1;
+    if (!cfg.seed) cfg.seed = 0xB200u;
+    if (!cfg.samples) cfg.samples = 1024;
+    if (cfg.samples < 1 || cfg.samples > (1 << 20)) { b200::set_error("gemm: samples out of range"); return B200PROBE_EINVAL; }
+    if (cfg.operands != B200PROBE_GEMM_OPERANDS_EXACT && cfg.operands != B200PROBE_GEMM_OPERANDS_UNIFORM) { b200::set_error("gemm: unknown operand class %d", cfg.operands); return B200PROBE_EINVAL; }
+    rc = check_shape(cfg.m, cfg.n, cfg.k);
+    if (rc) return rc;
+    memset(out, 0, sizeof(*out));
+    out->m = cfg.m; out->n = cfg.n; out->k = cfg.k;
+    out->operands = cfg.operands;
+    out->verified = -1;
+    B200_CUDA_TRY(cudaSetDevice(ordinal));
+    GemmArena& g = g_gemm[ordinal];
+    GemmLock lock(g);
+    rc = gemm_locked(ordinal, g, cfg, out);
+    if (rc && rc != B200PROBE_EMISMATCH) gemm_arena_free(g);      // unknown state after a CUDA error / failed allocation: start over next time
+    return rc;
 }
 
 }  // extern "C"

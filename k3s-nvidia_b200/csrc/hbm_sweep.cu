@@ -35,6 +35,10 @@ struct RingArgs {
     uint32_t stage_bytes;      // multiple of 512
     uint32_t stages;           // 2..kMaxStages
     unsigned long long* partials;   // [0] sum64, [1] xor (read mode); verify adds [2] mismatching words, [3] lowest mismatching word
+    // experiment knobs (environment only, never part of the ABI; 0 = the shipped behaviour):
+    int load_policy, store_policy;  // L2 eviction policy of the bulk loads / stores: 0 evict_first, 1 evict_normal, 2 evict_last, 3 evict_unchanged
+    int slab_map;                   // 1 = every worker owns one contiguous slab instead of every nworkers-th chunk
+    int batch;                      // copy: 1 = fill ALL stages, then store ALL stages (per-warp read and write phases)
 };
 
 __device__ __forceinline__ void accum16(const uint4& v, unsigned long long& sum, uint32_t& x) {
@@ -102,14 +106,17 @@ __global__ void __launch_bounds__(kMaxWarps * 32) hbm_ring_kernel(RingArgs a) {
     const uint64_t nchunks = (bulk_bytes + SB - 1) / SB;
     const uint64_t worker = (uint64_t)blockIdx.x * nwarps + warp;
     const uint64_t nworkers = (uint64_t)gridDim.x * nwarps;
-    const uint64_t n_my = worker < nchunks ? (nchunks - worker + nworkers - 1) / nworkers : 0;
+    const uint64_t n_my = a.slab_map ? (worker * ((nchunks + nworkers - 1) / nworkers) < nchunks
+                                            ? min((nchunks + nworkers - 1) / nworkers, nchunks - worker * ((nchunks + nworkers - 1) / nworkers)) : 0)
+                                     : (worker < nchunks ? (nchunks - worker + nworkers - 1) / nworkers : 0);
 
     const uint32_t ring = smem_u32(smem) + warp * S * SB;
     uint8_t* ring_ptr = smem + (size_t)warp * S * SB;
     const uint32_t bar0 = smem_u32(&full_bar[warp * kMaxStages]);
-    const uint64_t pol = policy_evict_first();
+    const uint64_t pol = policy_of(a.load_policy), pol_st = policy_of(a.store_policy);
+    const uint64_t slab = (nchunks + nworkers - 1) / nworkers;     // slab_map: chunks [worker*slab, +slab)
 
-    auto chunk_off = [&](uint64_t k) { return (worker + k * nworkers) * (uint64_t)SB; };
+    auto chunk_off = [&](uint64_t k) { return (a.slab_map ? worker * slab + k : worker + k * nworkers) * (uint64_t)SB; };
     auto chunk_len = [&](uint64_t k) { uint64_t o = chunk_off(k); return (uint32_t)min((uint64_t)SB, bulk_bytes - o); };
     // producer cursor (stage ps) and consumer cursor (stage cs, parity cph) advance without div/mod
     uint32_t ps = 0, cs = 0, cph = 0;
@@ -123,13 +130,28 @@ __global__ void __launch_bounds__(kMaxWarps * 32) hbm_ring_kernel(RingArgs a) {
     };
     auto advance = [&]() { if (++cs == S) { cs = 0; cph ^= 1; } };
 
-    if (MODE == B200PROBE_HBM_COPY) {
+    if (MODE == B200PROBE_HBM_COPY && a.batch) {
+        if (lane == 0) {
+            for (uint64_t k0 = 0; k0 < n_my; k0 += S) {           // read phase: S loads; write phase: S stores; repeat
+                const uint64_t n = min((uint64_t)S, n_my - k0);
+                for (uint64_t j = 0; j < n; ++j) load_next();
+                for (uint64_t j = 0; j < n; ++j) {
+                    mbar_wait(bar0 + cs * 8, cph);
+                    bulk_s2g(a.dst + chunk_off(k0 + j), ring + cs * SB, chunk_len(k0 + j), pol_st);
+                    advance();
+                }
+                bulk_commit();
+                bulk_wait_read<0>();
+            }
+            bulk_wait_all();
+        }
+    } else if (MODE == B200PROBE_HBM_COPY) {
         if (lane == 0 && n_my > 0) {
             const uint64_t ahead = min((uint64_t)(S - 1), n_my);
             while (issued < ahead) load_next();
             for (uint64_t k = 0; k < n_my; ++k) {
                 mbar_wait(bar0 + cs * 8, cph);
-                bulk_s2g(a.dst + chunk_off(k), ring + cs * SB, chunk_len(k), pol);
+                bulk_s2g(a.dst + chunk_off(k), ring + cs * SB, chunk_len(k), pol_st);
                 bulk_commit();
                 if (issued < n_my) {
                     bulk_wait_read<1>();       // store k-1 has drained its stage, which the next load reuses
@@ -213,7 +235,7 @@ __global__ void __launch_bounds__(kMaxWarps * 32) hbm_ring_kernel(RingArgs a) {
             fence_proxy_async_smem();          // generic-proxy writes -> visible to the async proxy
             __syncwarp();
             if (lane == 0) {
-                bulk_s2g(a.dst + chunk_off(k), ring + cs * SB, chunk_len(k), pol);
+                bulk_s2g(a.dst + chunk_off(k), ring + cs * SB, chunk_len(k), pol_st);
                 bulk_commit();
             }
             advance();
@@ -357,6 +379,11 @@ int check_args(const void* p0, const void* p1, uint64_t bytes) {
     return 0;
 }
 
+int env_int(const char* name) {
+    const char* e = getenv(name);
+    return e ? atoi(e) : 0;
+}
+
 template <int MODE>
 int launch_mode(int ordinal, RingArgs a, const b200probe_hbm_cfg_t* cfg, cudaStream_t stream) {
     b200::DevProps props;
@@ -378,6 +405,8 @@ int launch_mode(int ordinal, RingArgs a, const b200probe_hbm_cfg_t* cfg, cudaStr
         }
         a.stage_bytes = (uint32_t)t.stage_bytes;
         a.stages = (uint32_t)t.stages;
+        a.load_policy = env_int("B200PROBE_HBM_LOAD_POLICY"); a.store_policy = env_int("B200PROBE_HBM_STORE_POLICY");      // read per launch:
+        a.slab_map = env_int("B200PROBE_HBM_SLAB_MAP"); a.batch = env_int("B200PROBE_HBM_COPY_BATCH");                     // tools flip them in-process
         B200_CUDA_TRY(cudaFuncSetAttribute(hbm_ring_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         int grid = props.sms * t.ctas_per_sm;
         hbm_ring_kernel<MODE><<<grid, t.warps * 32, smem, stream>>>(a);
@@ -473,7 +502,7 @@ int launch_verify(int ordinal, const uint8_t* buf, uint64_t bytes, uint32_t seed
         B200_CUDA_TRY(cudaGetLastError());
         return 0;
     }
-    RingArgs a{buf, nullptr, bytes, seed, 0, 0, partials};
+    RingArgs a{buf, nullptr, bytes, seed, 0, 0, partials, 0, 0, 0, 0};
     return launch_mode<kModeVerify>(ordinal, a, nullptr, stream);
 }
 
@@ -522,14 +551,14 @@ extern "C" {
 int b200probe_hbm_fill(int ordinal, void* dst, uint64_t bytes, uint32_t seed, const b200probe_hbm_cfg_t* cfg, void* stream) {
     int rc = check_args(dst, nullptr, bytes);
     if (rc) return rc;
-    RingArgs a{nullptr, (uint8_t*)dst, bytes, seed, 0, 0, nullptr};
+    RingArgs a{nullptr, (uint8_t*)dst, bytes, seed, 0, 0, nullptr, 0, 0, 0, 0};
     return launch_mode<B200PROBE_HBM_WRITE>(ordinal, a, cfg, (cudaStream_t)stream);
 }
 
 int b200probe_hbm_copy(int ordinal, const void* src, void* dst, uint64_t bytes, const b200probe_hbm_cfg_t* cfg, void* stream) {
     int rc = check_args(src, dst, bytes);
     if (rc) return rc;
-    RingArgs a{(const uint8_t*)src, (uint8_t*)dst, bytes, 0, 0, 0, nullptr};
+    RingArgs a{(const uint8_t*)src, (uint8_t*)dst, bytes, 0, 0, 0, nullptr, 0, 0, 0, 0};
     return launch_mode<B200PROBE_HBM_COPY>(ordinal, a, cfg, (cudaStream_t)stream);
 }
 
@@ -537,7 +566,7 @@ int b200probe_hbm_read(int ordinal, const void* src, uint64_t bytes, uint64_t* p
     int rc = check_args(src, partials, bytes);
     if (rc) return rc;
     if (!partials) return B200PROBE_EINVAL;
-    RingArgs a{(const uint8_t*)src, nullptr, bytes, 0, 0, 0, (unsigned long long*)partials};
+    RingArgs a{(const uint8_t*)src, nullptr, bytes, 0, 0, 0, (unsigned long long*)partials, 0, 0, 0, 0};
     return launch_mode<B200PROBE_HBM_READ>(ordinal, a, cfg, (cudaStream_t)stream);
 }
 

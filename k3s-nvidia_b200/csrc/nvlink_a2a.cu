@@ -63,6 +63,8 @@ struct XArgs {
     int push_ctas;     // MIX_TMA: CTAs (of ctas_per_peer) in the push role
     uint32_t timeout_us;   // PUSH_SYNC: longest wait at a step barrier before the launch gives up synchronising
     int sync_every;        // PUSH_SYNC: a barrier before steps 1, 1+k, 1+2k, ... (k = 1: every step)
+    int drain;             // PUSH_SYNC: every warp waits for its bulk stores to COMPLETE before it arrives at a step barrier, and the
+                           // last CTA to arrive stamps the step's end: start_ns/done_ns then bracket exactly one pair's bytes on the wire
 };
 
 // Sync page at window + 2*world*S (zeroed when the window is created).  flag[q] is written by rank q with a
@@ -73,14 +75,16 @@ struct SyncPage {
     uint32_t flag[kMaxWorld];
     uint32_t cnt;
     uint32_t epoch;
-    // PUSH_SYNC, barrier before every step: this device's %globaltimer when it left barrier b (= start of step b+1),
-    // and in slot world-1 when CTA 0 had drained its last store.  Step t moves exactly one pair, rank -> (rank+t) mod G,
-    // so consecutive differences are per-pair transfer times measured under the full exchange.
-    unsigned long long step_ns[kMaxWorld + 1];
-    // the same clock when the LAST CTA of the grid had drained its stores (CTA 0 alone finishes a little early, which
-    // made the last step of every rank look 5-50 % faster than the others: profiles/a2a_pair_matrix_r01_g4.txt)
+    // PUSH_SYNC with a barrier before every step.  Step t (1..world-1) moves exactly one pair, rank -> (rank+t) mod G.
+    //   start_ns[t]  this device's %globaltimer when CTA 0 left the barrier in front of step t
+    //   done_ns[t]   the same clock when the LAST CTA of the grid had seen its bulk stores of step t complete
+    //                (cp.async.bulk.wait_group 0).  Written for every step in drain mode, for the last step always.
+    // Only a drained step gives a pair rate: without the drain a step "ends" when its stores were ISSUED, and up to
+    // SMs x ring bytes (19 MB) of it are still in flight, which made pairs read above the link rate
+    // (profiles/a2a_pair_matrix_r01_g4.txt: 1050 GB/s on a 900 GB/s port).
+    unsigned long long start_ns[kMaxWorld];
+    unsigned long long done_ns[kMaxWorld];
     unsigned int done_cnt;
-    unsigned long long end_ns;
 };
 static_assert(sizeof(SyncPage) <= B200PROBE_A2A_SYNC_BYTES, "sync page");
 
@@ -220,10 +224,19 @@ __global__ void __launch_bounds__(kRingWarps * 32) a2a_stagger_kernel(XArgs a) {
             // up synchronising for the rest of the launch (a peer that never launched must not hang the GPU).
             const uint32_t b = (uint32_t)((t - 1) / a.sync_every), nb = (uint32_t)((a.world - 2) / a.sync_every + 1);
             const uint32_t target = epoch * 16u + b + 1u;
-            __syncthreads();                    // every warp of this CTA has issued its stores of the step before
+            if (a.drain && t >= 2) {            // step t-1 is over for this warp only when its stores have landed
+                if (lane == 0) bulk_wait_all();
+                __syncwarp();
+            }
+            __syncthreads();                    // every warp of this CTA has issued (drain: completed) its stores of the step before
             if (threadIdx.x == 0) {
                 const uint32_t n = atomicAdd(&mine->cnt, 1u);
                 if (n == gridDim.x * (b + 1) - 1) {
+                    if (a.drain && t >= 2) {    // last CTA of this rank to finish step t-1
+                        unsigned long long now_ns;
+                        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now_ns));
+                        mine->done_ns[t - 1] = now_ns;
+                    }
                     if (b + 1 == nb) { atomicExch(&mine->cnt, 0u); atomicExch(&mine->epoch, epoch + 1u); }   // last barrier of the launch
                     for (int q = 0; q < a.world; ++q) {
                         SyncPage* theirs = reinterpret_cast<SyncPage*>(a.peers.win[q] + 2ull * a.world * S);
@@ -253,7 +266,7 @@ __global__ void __launch_bounds__(kRingWarps * 32) a2a_stagger_kernel(XArgs a) {
                 if (blockIdx.x == 0 && lane == 0 && a.sync_every == 1) {
                     unsigned long long now_ns;
                     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now_ns));
-                    mine->step_ns[b] = now_ns;
+                    mine->start_ns[t] = ok ? now_ns : 0ull;      // 0: this launch lost the barrier, its stamps mean nothing
                 }
             }
             __syncthreads();
@@ -283,13 +296,12 @@ __global__ void __launch_bounds__(kRingWarps * 32) a2a_stagger_kernel(XArgs a) {
     }
     if (lane == 0) bulk_wait_all();
     if (sync && a.sync_every == 1) {
-        __syncthreads();                                   // every warp of this CTA has drained its stores
+        __syncthreads();                                   // every warp of this CTA has seen its stores complete
         if (threadIdx.x == 0) {
-            unsigned long long now_ns;
-            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now_ns));
-            if (blockIdx.x == 0) mine->step_ns[a.world - 1] = now_ns;
-            if (atomicAdd(&mine->done_cnt, 1u) == gridDim.x - 1) {          // last CTA of the grid: the exchange is over
-                mine->end_ns = now_ns;
+            if (atomicAdd(&mine->done_cnt, 1u) == gridDim.x - 1) {          // last CTA of the grid: the last step (and the exchange) is over
+                unsigned long long now_ns;
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now_ns));
+                mine->done_ns[a.world - 1] = now_ns;
                 atomicExch(&mine->done_cnt, 0u);
             }
         }
@@ -339,7 +351,7 @@ int auto_exchange_variant(int world, uint64_t S, bool gated = false) {
 }
 
 int launch_exchange(int ordinal, int rank, int world, void* const* windows, uint64_t S, uint32_t seed, int variant, int ctas_per_peer,
-                    int only_peer, cudaStream_t stream) {
+                    int only_peer, cudaStream_t stream, bool drain = false) {
     if (world < 1 || world > kMaxWorld || rank < 0 || rank >= world || !windows) { b200::set_error("a2a: bad rank/world"); return B200PROBE_EINVAL; }
     if (S & 15) { b200::set_error("a2a: bytes_per_pair must be a multiple of 16"); return B200PROBE_EINVAL; }
     if (variant < 0 || variant > B200PROBE_A2A_PUSH_SYNC) { b200::set_error("a2a: unknown variant %d", variant); return B200PROBE_EINVAL; }
@@ -382,6 +394,7 @@ int launch_exchange(int ordinal, int rank, int world, void* const* windows, uint
                 grid = std::min(grid, props.sms);                                // the barrier needs every CTA resident (1 CTA/SM at this ring size)
                 a.timeout_us = 200000;
                 a.sync_every = 1;
+                a.drain = drain ? 1 : 0;
                 if (const char* e = getenv("B200PROBE_A2A_SYNC_EVERY")) { int v = atoi(e); if (v >= 1 && v <= kMaxWorld) a.sync_every = v; }
                 if (const char* e = getenv("B200PROBE_A2A_SYNC_TIMEOUT_US")) { int v = atoi(e); if (v > 0) a.timeout_us = (uint32_t)v; }
             }
@@ -440,12 +453,25 @@ struct PerDev {
     cudaEvent_t e0 = nullptr, e1 = nullptr;
 };
 
+// Resident per-process exchange context: windows (send halves filled), streams, events, the start gate and the NCCL
+// communicators of the library leg stay alive between calls with the same (devices, S, seed) — a probe round calls the
+// entry several times (exchange, pair matrix, library contrast) and cudaMalloc of 4 GiB per device plus ncclCommInitAll
+// cost far more than the exchange.  Freed by b200probe_a2a_release(), or replaced when the key changes.
 struct A2aCtx {
+    int g = 0;
+    int ordinals[kMaxWorld] = {0};
+    uint64_t S = 0;
+    uint32_t seed = 0;
     std::vector<PerDev> d;
     uint32_t* gate_host = nullptr;      // mapped pinned word the gate kernels spin on
     uint32_t gate_epoch = 0;
     Nccl nccl;
     std::vector<ncclComm_t> comms;
+    bool matches(const int* o, int n, uint64_t s, uint32_t sd) const {
+        if (n != g || s != S || sd != seed) return false;
+        for (int i = 0; i < n; ++i) if (o[i] != ordinals[i]) return false;
+        return true;
+    }
     ~A2aCtx() {
         for (auto c : comms) if (c && nccl.lib) nccl.CommDestroy(c);
         for (auto& p : d) {
@@ -460,6 +486,60 @@ struct A2aCtx {
         if (nccl.lib) dlclose(nccl.lib);
         if (gate_host) cudaFreeHost(gate_host);
     }
+};
+pthread_mutex_t g_ctx_mu = PTHREAD_MUTEX_INITIALIZER;     // also serialises the cross-device calls (header: "serialise internally")
+A2aCtx* g_ctx = nullptr;
+
+// a failed cudaMalloc is a RESOURCE verdict (a tenant holds the memory), not a CUDA fault: the host must be able to tell
+#define B200_ALLOC_TRY(expr)                                                                                  \
+    do {                                                                                                      \
+        cudaError_t e__ = (expr);                                                                             \
+        if (e__ == cudaErrorMemoryAllocation) { cudaGetLastError(); b200::set_error("%s: out of device memory", #expr); return B200PROBE_ENOMEM; } \
+        if (e__ != cudaSuccess) { b200::set_error("%s:%d %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(e__)); return b200::cuda_rc((int)e__); } \
+    } while (0)
+
+int ctx_build(A2aCtx* c, const int* ordinals, int g, uint64_t S, uint32_t seed) {
+    c->g = g; c->S = S; c->seed = seed;
+    for (int i = 0; i < g; ++i) c->ordinals[i] = ordinals[i];
+    c->d.resize(g);
+    for (int i = 0; i < g; ++i) {
+        B200_CUDA_TRY(cudaSetDevice(ordinals[i]));
+        PerDev& p = c->d[i];
+        p.ordinal = ordinals[i];
+        B200_CUDA_TRY(cudaStreamCreateWithFlags(&p.stream, cudaStreamNonBlocking));
+        B200_CUDA_TRY(cudaEventCreate(&p.e0));
+        B200_CUDA_TRY(cudaEventCreate(&p.e1));
+        B200_ALLOC_TRY(cudaMalloc(&p.window, 2ull * g * S + B200PROBE_A2A_SYNC_BYTES));
+        B200_ALLOC_TRY(cudaMalloc(&p.partials, 32));
+        int rc = fill_send_half(p.ordinal, p.window, i, g, S, seed, p.stream);
+        if (rc) return rc;
+    }
+    B200_CUDA_TRY(cudaHostAlloc((void**)&c->gate_host, 64, cudaHostAllocPortable | cudaHostAllocMapped));
+    *c->gate_host = 0;
+    for (int i = 0; i < g; ++i) {
+        B200_CUDA_TRY(cudaSetDevice(ordinals[i]));
+        B200_CUDA_TRY(cudaStreamSynchronize(c->d[i].stream));
+    }
+    return 0;
+}
+
+// the context for this key, built or reused; g_ctx_mu held by the caller
+int ctx_acquire(const int* ordinals, int g, uint64_t S, uint32_t seed, A2aCtx** out) {
+    if (g_ctx && !g_ctx->matches(ordinals, g, S, seed)) { delete g_ctx; g_ctx = nullptr; }
+    if (!g_ctx) {
+        A2aCtx* c = new A2aCtx();
+        int rc = ctx_build(c, ordinals, g, S, seed);
+        if (rc) { delete c; return rc; }
+        g_ctx = c;
+    }
+    *out = g_ctx;
+    return 0;
+}
+
+struct MutexLock {
+    pthread_mutex_t* m;
+    explicit MutexLock(pthread_mutex_t* x) : m(x) { pthread_mutex_lock(m); }
+    ~MutexLock() { pthread_mutex_unlock(m); }
 };
 
 double median_of(std::vector<double> v) {
@@ -555,7 +635,14 @@ int b200probe_a2a_exchange(int ordinal, int rank, int world, void* const* window
     return launch_exchange(ordinal, rank, world, windows, S, seed, variant, ctas_per_peer, only_peer, (cudaStream_t)stream);
 }
 
-int b200probe_nvlink_a2a(const int* ordinals, int g, const b200probe_a2a_cfg_t* cfg_in, double* pair_gbs, b200probe_a2a_result_t* out) {
+int b200probe_a2a_release(void) {
+    MutexLock lock(&g_ctx_mu);
+    delete g_ctx;
+    g_ctx = nullptr;
+    return 0;
+}
+
+static int nvlink_a2a_locked(const int* ordinals, int g, const b200probe_a2a_cfg_t* cfg_in, double* pair_gbs, b200probe_a2a_result_t* out) {
     if (!ordinals || g < 2 || g > kMaxWorld || !out) { b200::set_error("nvlink_a2a: need 2..%d devices", kMaxWorld); return B200PROBE_EINVAL; }
     b200probe_a2a_cfg_t cfg;
     memset(&cfg, 0, sizeof(cfg));
@@ -566,48 +653,40 @@ int b200probe_nvlink_a2a(const int* ordinals, int g, const b200probe_a2a_cfg_t* 
     if (!cfg.seed) cfg.seed = 0xB200u;
     const uint64_t S = cfg.bytes_per_pair;
     if (S & 15) { b200::set_error("a2a: bytes_per_pair must be a multiple of 16"); return B200PROBE_EINVAL; }
+    if (cfg.mode < B200PROBE_A2A_PEER_ALL || cfg.mode > B200PROBE_A2A_CE) { b200::set_error("a2a: unknown mode %d", cfg.mode); return B200PROBE_EINVAL; }
     memset(out, 0, sizeof(*out));
     out->g = g;
     out->verified = -1;
     if (pair_gbs) std::fill(pair_gbs, pair_gbs + g * g, 0.0);
-    const bool nccl_mode = cfg.mode == B200PROBE_A2A_NCCL;
-    const bool gated = !nccl_mode && cfg.mode == B200PROBE_A2A_PEER_ALL && !getenv("B200PROBE_A2A_NO_GATE");
+    const bool nccl_mode = cfg.mode == B200PROBE_A2A_NCCL, ce_mode = cfg.mode == B200PROBE_A2A_CE;
+    const bool library = nccl_mode || ce_mode;
+    const bool gated = !nccl_mode && cfg.mode != B200PROBE_A2A_PEER_PAIR && !getenv("B200PROBE_A2A_NO_GATE");
     if (cfg.variant == B200PROBE_A2A_AUTO) cfg.variant = cfg.mode == B200PROBE_A2A_PEER_PAIR ? B200PROBE_A2A_PULL_TMA : auto_exchange_variant(g, cfg.bytes_per_pair, gated);
     if (cfg.variant == B200PROBE_A2A_MIX_TMA && cfg.mode == B200PROBE_A2A_PEER_PAIR) cfg.variant = B200PROBE_A2A_PULL_TMA;
-    const bool pull = !nccl_mode && cfg.variant == B200PROBE_A2A_PULL_TMA;
-    const bool mix = !nccl_mode && cfg.variant == B200PROBE_A2A_MIX_TMA;
+    const bool pull = !library && cfg.variant == B200PROBE_A2A_PULL_TMA;
+    const bool mix = !library && cfg.variant == B200PROBE_A2A_MIX_TMA;
 
     int rc = b200probe_enable_peer_access(ordinals, g);
     if (rc) return rc;
-    A2aCtx ctx;
-    ctx.d.resize(g);
+    A2aCtx* ctxp = nullptr;
+    rc = ctx_acquire(ordinals, g, S, cfg.seed, &ctxp);
+    if (rc) return rc;
+    A2aCtx& ctx = *ctxp;
+    // every call starts from empty recv slots (what verification finds there landed during THIS call) and a clean sync page
     for (int i = 0; i < g; ++i) {
-        B200_CUDA_TRY(cudaSetDevice(ordinals[i]));
-        PerDev& p = ctx.d[i];
-        p.ordinal = ordinals[i];
-        B200_CUDA_TRY(cudaStreamCreateWithFlags(&p.stream, cudaStreamNonBlocking));
-        B200_CUDA_TRY(cudaEventCreate(&p.e0));
-        B200_CUDA_TRY(cudaEventCreate(&p.e1));
-        B200_CUDA_TRY(cudaMalloc(&p.window, 2ull * g * S + B200PROBE_A2A_SYNC_BYTES));
-        B200_CUDA_TRY(cudaMemsetAsync(p.window, 0, (size_t)g * S, p.stream));
-        B200_CUDA_TRY(cudaMemsetAsync(p.window + 2ull * g * S, 0, B200PROBE_A2A_SYNC_BYTES, p.stream));
-        B200_CUDA_TRY(cudaMalloc(&p.partials, 32));
-        rc = fill_send_half(p.ordinal, p.window, i, g, S, cfg.seed, p.stream);
-        if (rc) return rc;
-        B200_CUDA_TRY(cudaStreamSynchronize(p.stream));
+        B200_CUDA_TRY(cudaSetDevice(ctx.d[i].ordinal));
+        B200_CUDA_TRY(cudaMemsetAsync(ctx.d[i].window, 0, (size_t)g * S, ctx.d[i].stream));
+        B200_CUDA_TRY(cudaMemsetAsync(ctx.d[i].window + 2ull * g * S, 0, B200PROBE_A2A_SYNC_BYTES, ctx.d[i].stream));
     }
     void* windows[kMaxWorld] = {nullptr};
     for (int i = 0; i < g; ++i) windows[i] = ctx.d[i].window;
-    if (gated) {
-        B200_CUDA_TRY(cudaHostAlloc((void**)&ctx.gate_host, 64, cudaHostAllocPortable | cudaHostAllocMapped));
-        *ctx.gate_host = 0;
-    }
 
-    if (nccl_mode) {
+    if (nccl_mode && ctx.comms.empty()) {
         rc = load_nccl(&ctx.nccl);
         if (rc) return rc;
         ctx.comms.assign(g, nullptr);
-        NCCL_TRY(ctx.nccl, ctx.nccl.CommInitAll(ctx.comms.data(), g, ordinals));
+        int r = ctx.nccl.CommInitAll(ctx.comms.data(), g, ordinals);
+        if (r != 0) { ctx.comms.clear(); b200::set_error("ncclCommInitAll -> %s", ctx.nccl.GetErrorString(r)); return B200PROBE_NCCL_BASE + r; }
     }
 
     auto sync_all = [&]() -> int {
@@ -617,8 +696,10 @@ int b200probe_nvlink_a2a(const int* ordinals, int g, const b200probe_a2a_cfg_t* 
         }
         return 0;
     };
+    rc = sync_all();
+    if (rc) return rc;
     // one all-pairs exchange; per-device elapsed ms into t[]
-    auto exchange = [&](bool timed, std::vector<double>* t) -> int {
+    auto exchange = [&](bool timed, std::vector<double>* t, bool drain) -> int {
         const uint32_t release = ++ctx.gate_epoch;
         struct Release {                                   // whatever path leaves this function, no gate kernel is left spinning
             uint32_t* word; uint32_t v;
@@ -633,9 +714,17 @@ int b200probe_nvlink_a2a(const int* ordinals, int g, const b200probe_a2a_cfg_t* 
                 B200_CUDA_TRY(cudaGetLastError());
             }
             if (timed) B200_CUDA_TRY(cudaEventRecord(ctx.d[i].e0, ctx.d[i].stream));
-            if (!nccl_mode) {
+            if (ce_mode) {
+                // library leg 2: the copy engines push every chunk (cudaMemcpyPeerAsync), peers in the rotation (i+t) mod G
+                for (int t = 1; t < g; ++t) {
+                    const int j = (i + t) % g;
+                    B200_CUDA_TRY(cudaMemcpyPeerAsync(ctx.d[j].window + (size_t)i * S, ctx.d[j].ordinal, ctx.d[i].window + ((size_t)g + j) * S,
+                                                      ctx.d[i].ordinal, S, ctx.d[i].stream));
+                }
+                if (timed) B200_CUDA_TRY(cudaEventRecord(ctx.d[i].e1, ctx.d[i].stream));
+            } else if (!nccl_mode) {
                 // -2: the local slot is HBM traffic, not NVLink: kept out of the timed exchange
-                int r2 = launch_exchange(ctx.d[i].ordinal, i, g, windows, S, cfg.seed, cfg.variant, cfg.ctas_per_peer, -2, ctx.d[i].stream);
+                int r2 = launch_exchange(ctx.d[i].ordinal, i, g, windows, S, cfg.seed, cfg.variant, cfg.ctas_per_peer, -2, ctx.d[i].stream, drain);
                 if (r2) return r2;
                 if (timed) B200_CUDA_TRY(cudaEventRecord(ctx.d[i].e1, ctx.d[i].stream));
             }
@@ -703,12 +792,13 @@ int b200probe_nvlink_a2a(const int* ordinals, int g, const b200probe_a2a_cfg_t* 
                 mn = std::min(mn, gbs); mx = std::max(mx, gbs);
             }
         out->min_pair_gbs = mn; out->max_pair_gbs = mx;
+        out->pair_source = B200PROBE_PAIR_ISOLATED;
     } else {
         std::vector<std::vector<double>> per_dev(g);
         std::vector<double> wall;
         for (int it = -cfg.warmup; it < cfg.reps; ++it) {
             std::vector<double> t;
-            rc = exchange(it >= 0, &t);
+            rc = exchange(it >= 0, &t, false);
             if (rc) return rc;
             if (it >= 0) {
                 for (int i = 0; i < g; ++i) per_dev[i].push_back(t[i]);
@@ -718,23 +808,30 @@ int b200probe_nvlink_a2a(const int* ordinals, int g, const b200probe_a2a_cfg_t* 
         out->ms_median = median_of(wall);
         out->ms_best = *std::min_element(wall.begin(), wall.end());
         const double payload = (double)(g - 1) * (double)S;
-        double mn = 1e300, mx = 0;
-        // PUSH_SYNC with a barrier before every step: the kernel stamped each step, and a step moves one pair alone
-        // (rank -> (rank+t) mod G), so the matrix holds real per-pair rates of the last exchange instead of shares.
-        std::vector<std::vector<unsigned long long>> stamps;
-        if (cfg.variant == B200PROBE_A2A_PUSH_SYNC && !getenv("B200PROBE_A2A_SYNC_EVERY")) {
-            stamps.assign(g, std::vector<unsigned long long>(kMaxWorld + 1, 0));
-            for (int i = 0; i < g; ++i) {
-                B200_CUDA_TRY(cudaSetDevice(ctx.d[i].ordinal));
-                SyncPage page;
-                B200_CUDA_TRY(cudaMemcpy(&page, ctx.d[i].window + 2ull * g * S, sizeof(page), cudaMemcpyDeviceToHost));
-                for (int t = 0; t <= kMaxWorld; ++t) stamps[i][t] = page.step_ns[t];
-                if (page.end_ns > stamps[i][g - 1]) stamps[i][g - 1] = page.end_ns;      // end of the last step = the last CTA's drain, not CTA 0's
-                bool ordered = true;
-                for (int t = 1; t < g; ++t) ordered = ordered && stamps[i][t] > stamps[i][t - 1];
-                if (!ordered) { stamps.clear(); break; }                                 // a launch that lost the barrier: fall back to shares
+        // Pair matrix of the stepped exchange (PUSH_SYNC, a barrier before every step): a step moves one pair per rank alone
+        // (rank -> (rank+t) mod G).  The timed exchanges above run the steps back to back WITHOUT draining (that is the
+        // headline rate); the matrix comes from extra exchanges in drain mode, where a step starts when every rank's previous
+        // step has landed and ends when this rank's last store has completed: S bytes / (done - start) is that pair's own
+        // rate with nothing else of this rank on the wire, and it cannot exceed the port rate.
+        std::vector<std::vector<std::vector<double>>> stepped;      // [i][t] -> GB/s samples
+        if (!library && cfg.variant == B200PROBE_A2A_PUSH_SYNC && g > 2 && !getenv("B200PROBE_A2A_SYNC_EVERY")) {
+            stepped.assign(g, std::vector<std::vector<double>>(g));
+            const int kMatrixReps = 3;
+            for (int rep = 0; rep < kMatrixReps && !stepped.empty(); ++rep) {
+                rc = exchange(false, nullptr, true);
+                if (rc) return rc;
+                for (int i = 0; i < g && !stepped.empty(); ++i) {
+                    B200_CUDA_TRY(cudaSetDevice(ctx.d[i].ordinal));
+                    SyncPage page;
+                    B200_CUDA_TRY(cudaMemcpy(&page, ctx.d[i].window + 2ull * g * S, sizeof(page), cudaMemcpyDeviceToHost));
+                    for (int t = 1; t < g; ++t) {
+                        if (!page.start_ns[t] || page.done_ns[t] <= page.start_ns[t]) { stepped.clear(); break; }     // a launch that lost the barrier: shares
+                        stepped[i][t].push_back((double)S / (double)(page.done_ns[t] - page.start_ns[t]));          // bytes per ns = GB/s
+                    }
+                }
             }
         }
+        double mn = 1e300, mx = 0;
         for (int i = 0; i < g; ++i) {
             const double own = payload / (median_of(per_dev[i]) * 1e-3) / 1e9;      // the direction rank i's kernel drives
             const double common = payload / (out->ms_median * 1e-3) / 1e9;          // the other direction, over the common window
@@ -743,15 +840,13 @@ int b200probe_nvlink_a2a(const int* ordinals, int g, const b200probe_a2a_cfg_t* 
             for (int j = 0; j < g; ++j) {
                 if (i == j) continue;
                 double gbs = own / (g - 1);                                         // per-pair share under full concurrency
-                if (!stamps.empty()) {
-                    const int t = (j - i + g) % g;                                  // pair i -> j is step t of rank i
-                    gbs = (double)S / (double)(stamps[i][t] - stamps[i][t - 1]);      // bytes per ns = GB/s
-                }
+                if (!stepped.empty()) gbs = median_of(stepped[i][(j - i + g) % g]);  // pair i -> j is step (j-i) mod G of rank i
                 if (pair_gbs) pair_gbs[pull ? j * g + i : i * g + j] = gbs;
                 mn = std::min(mn, gbs); mx = std::max(mx, gbs);
             }
         }
         out->min_pair_gbs = mn; out->max_pair_gbs = mx;
+        out->pair_source = stepped.empty() ? B200PROBE_PAIR_SHARE : B200PROBE_PAIR_STEPPED;
     }
     rc = local_slots();
     if (rc) return rc;
@@ -778,6 +873,16 @@ int b200probe_nvlink_a2a(const int* ordinals, int g, const b200probe_a2a_cfg_t* 
         if (!ok) return B200PROBE_EMISMATCH;
     }
     return 0;
+}
+
+int b200probe_nvlink_a2a(const int* ordinals, int g, const b200probe_a2a_cfg_t* cfg, double* pair_gbs, b200probe_a2a_result_t* out) {
+    MutexLock lock(&g_ctx_mu);
+    const int rc = nvlink_a2a_locked(ordinals, g, cfg, pair_gbs, out);
+    if (rc && rc != B200PROBE_EMISMATCH) {      // a failed call leaves streams / windows in an unknown state: start over next time
+        delete g_ctx;
+        g_ctx = nullptr;
+    }
+    return rc;
 }
 
 }  // extern "C"

@@ -59,6 +59,16 @@ __device__ __forceinline__ uint64_t policy_evict_first() {
     asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
     return p;
 }
-
+// 0 evict_first (streamed once: the default everywhere), 1 evict_normal, 2 evict_last, 3 evict_unchanged
+__device__ __forceinline__ uint64_t policy_of(int kind) {
+    uint64_t p;
+    switch (kind) {
+        case 1: asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(p)); break;
+        case 2: asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p)); break;
+        case 3: asm volatile("createpolicy.fractional.L2::evict_unchanged.b64 %0, 1.0;" : "=l"(p)); break;
+        default: asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p)); break;
+    }
+    return p;
+}
 
 }  // namespace b200ptx

@@ -43,6 +43,25 @@ def barrier() -> None:
         dist.barrier()
 
 
+_host_group = None
+
+
+def host_barrier() -> None:
+    """A barrier that keeps the GPUs idle while ranks wait.  dist.barrier() on NCCL parks an all-reduce kernel on every
+    waiting rank's GPU; while rank 0 alone drives ALL GPUs through the single-process plugin entry (the step barrier of
+    the exchange kernel needs every CTA of every device resident) nothing else may sit on their SMs.  Uses a gloo group
+    over the same ranks, created on first use (collectively: every rank must call this the same number of times)."""
+    global _host_group
+    if not dist.is_initialized():
+        return
+    if dist.get_backend() != "nccl":
+        dist.barrier()
+        return
+    if _host_group is None:
+        _host_group = dist.new_group(backend="gloo")
+    dist.barrier(group=_host_group)
+
+
 def reduce_scalar(x: float, op: str = "max") -> float:
     if not dist.is_initialized():
         return float(x)

@@ -61,6 +61,7 @@ class A2aReport:
     min_pair_gbs: float
     max_pair_gbs: float
     verified: int
+    pair_source: int = 0       # _lib.PAIR_SHARE / PAIR_ISOLATED / PAIR_STEPPED
 
 
 @dataclass
@@ -80,6 +81,8 @@ class GemmReport:
     c_sum64: int
     c_xor32: int
     verified: int
+    operands: int = 0            # _lib.GEMM_EXACT / GEMM_UNIFORM
+    max_err_over_tol: float = 0.0
 
 
 @dataclass
@@ -168,6 +171,12 @@ class Probe:
 
     def health_close(self) -> None:
         self.lib.b200probe_health_close()
+
+    # -- is somebody else on the device? ---------------------------------------------------------------
+    def device_busy(self, idx: int) -> dict:
+        b = L.Busy()
+        self._check(self.lib.b200probe_device_busy(idx, C.byref(b)), "device_busy")
+        return {f: getattr(b, f) for f, _ in L.Busy._fields_}
 
     # -- passive NVLink ------------------------------------------------------------------------------
     def nvlink_passive(self, idx: int) -> dict:
@@ -258,14 +267,26 @@ class Probe:
         self._check(rc, "nvlink_a2a")
         return A2aReport(g, res.ms_median, res.ms_best, list(res.egress_gbs[:g]), list(res.ingress_gbs[:g]),
                          [[pair[i * g + j] for j in range(g)] for i in range(g)], res.min_pair_gbs, res.max_pair_gbs,
-                         res.verified)
+                         res.verified, res.pair_source)
+
+    def a2a_release(self) -> None:
+        """Free the resident exchange context (windows, streams, NCCL communicators)."""
+        self._check(self.lib.b200probe_a2a_release(), "a2a_release")
 
     # -- GEMM ------------------------------------------------------------------------------------
-    def gemm(self, idx: int = 0, *, m=0, n=0, k=0, warmup=0, reps=0, seed=0xB200, samples=0, sustain_seconds=0.0) -> GemmReport:
-        cfg = L.GemmCfg(m, n, k, warmup, reps, seed, samples, sustain_seconds)
+    def gemm(self, idx: int = 0, *, m=0, n=0, k=0, warmup=0, reps=0, seed=0xB200, samples=0, sustain_seconds=0.0, operands=L.GEMM_EXACT) -> GemmReport:
+        cfg = L.GemmCfg(m, n, k, warmup, reps, seed, samples, operands, sustain_seconds)
         r = L.GemmResult()
         rc = self.lib.b200probe_gemm(idx, C.byref(cfg), C.byref(r))
         rep = GemmReport(r.m, r.n, r.k, r.ms_median, r.ms_best, r.tflops_median, r.tflops_best, r.tflops_sustained,
-                         r.max_abs_err, r.max_rel_err, r.samples, r.bad, r.c_sum64, r.c_xor32, r.verified)
+                         r.max_abs_err, r.max_rel_err, r.samples, r.bad, r.c_sum64, r.c_xor32, r.verified, r.operands, r.max_err_over_tol)
         self._check(rc, "gemm")
         return rep
+
+    def release(self, ordinals: Sequence[int] = ()) -> None:
+        """Free every resident probe arena (HBM, GEMM per listed CUDA ordinal; the exchange context): what the plugin
+        does after a probe round, so the daemon holds no device memory while tenants run."""
+        for o in ordinals:
+            self.lib.b200probe_hbm_release(o)
+            self.lib.b200probe_gemm_release(o)
+        self.lib.b200probe_a2a_release()

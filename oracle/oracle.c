@@ -10,13 +10,16 @@
  * un-vendored.  What this file restates instead:
  *   - the synthetic data contract of SURVEY.md §8d  (u32 counter pattern x[i] = i*2654435761 ^ seed,
  *     seed 0xB200; checksum = sum mod 2^64 and xor of the u32 words),
- *   - the NVLink chunk-seed rule and the GEMM operand generator + fp64 contraction,
+ *   - the NVLink chunk-seed rule and the GEMM operand generators + fp64 contraction (class EXACT: k/128 values;
+ *     class UNIFORM: SURVEY.md §8d's "bf16 A,B ~ U(-1,1) from Philox seed 0xB200" — Philox4x32-10 restated from the
+ *     published algorithm and PINNED to the Random123 known-answer vectors in tests/test_oracle_golden.py),
  * written independently of k3s-nvidia_b200/csrc (no shared header), so a transcription error in
  * either shows up as a parity failure.  The passive-health twin is in passive_health_oracle.c.
  */
 #define _GNU_SOURCE
 #include <math.h>
 #include <pthread.h>
+#include <sched.h>
 #include <stdint.h>
 #include <stdlib.h>
 #include <string.h>
@@ -71,10 +74,17 @@ typedef struct {
     int mode, reps;
     uint64_t sum;
     uint32_t x;
+    int cpu;        /* >= 0: pin this thread there, so first touch and every timed pass of a slice run on the same NUMA node */
 } slice_t;
 
 static void* slice_run(void* p) {
     slice_t* s = (slice_t*)p;
+    if (s->cpu >= 0) {
+        cpu_set_t one;
+        CPU_ZERO(&one);
+        CPU_SET(s->cpu, &one);
+        pthread_setaffinity_np(pthread_self(), sizeof(one), &one);
+    }
     for (int r = 0; r < s->reps; ++r) {
         if (s->mode == 1) {
             uint64_t a; uint32_t b;
@@ -99,9 +109,29 @@ static double now_s(void) {
  * Returns seconds for the timed passes (buffers are allocated + first-touched outside the timing);
  * the data result of the last pass is returned through sum64/xor32 (read: checksum of src;
  * write/copy: checksum of dst). */
+static double host_sweep(uint64_t bytes, int threads, int mode, int reps, uint32_t seed, uint64_t* sum64, uint32_t* xor32, int pin);
 double oracle_host_sweep(uint64_t bytes, int threads, int mode, int reps, uint32_t seed, uint64_t* sum64, uint32_t* xor32) {
+    return host_sweep(bytes, threads, mode, reps, seed, sum64, xor32, 0);
+}
+/* the same sweep with thread t pinned to the t-th CPU of the process's allowed set (reproducible across boxes: the
+ * unpinned figure moved 40 -> 208 GB/s between two hosts in round 1) */
+double oracle_host_sweep_pinned(uint64_t bytes, int threads, int mode, int reps, uint32_t seed, uint64_t* sum64, uint32_t* xor32) {
+    return host_sweep(bytes, threads, mode, reps, seed, sum64, xor32, 1);
+}
+int oracle_allowed_cpus(void) {
+    cpu_set_t allowed;
+    if (sched_getaffinity(0, sizeof(allowed), &allowed)) return 1;
+    return CPU_COUNT(&allowed);
+}
+static double host_sweep(uint64_t bytes, int threads, int mode, int reps, uint32_t seed, uint64_t* sum64, uint32_t* xor32, int pin) {
     uint64_t words = bytes / 4;
     if (threads < 1) threads = 1;
+    int cpus[1024], ncpu = 0;
+    if (pin) {
+        cpu_set_t allowed;
+        if (!sched_getaffinity(0, sizeof(allowed), &allowed))
+            for (int c = 0; c < CPU_SETSIZE && ncpu < 1024; ++c) if (CPU_ISSET(c, &allowed)) cpus[ncpu++] = c;
+    }
     uint32_t* src = (uint32_t*)aligned_alloc(4096, (bytes + 4095) & ~4095ull);
     uint32_t* dst = (uint32_t*)aligned_alloc(4096, (bytes + 4095) & ~4095ull);
     if (!src || !dst) { free(src); free(dst); return -1.0; }
@@ -111,7 +141,7 @@ double oracle_host_sweep(uint64_t bytes, int threads, int mode, int reps, uint32
     /* first touch in parallel with the same slicing (NUMA placement), untimed */
     for (int t = 0; t < threads; ++t) {
         uint64_t f = per * t, w = f >= words ? 0 : (words - f < per ? words - f : per);
-        sl[t] = (slice_t){src, src, f, w, seed, 2, 1, 0, 0};
+        sl[t] = (slice_t){src, src, f, w, seed, 2, 1, 0, 0, ncpu ? cpus[t % ncpu] : -1};
         pthread_create(&th[t], NULL, slice_run, &sl[t]);
     }
     for (int t = 0; t < threads; ++t) pthread_join(th[t], NULL);
@@ -169,3 +199,50 @@ uint16_t oracle_bf16_rne(float f) {
     uint32_t r = 0x7fffu + ((u >> 16) & 1u);
     return (uint16_t)((u + r) >> 16);
 }
+
+/* ---- GEMM operand class UNIFORM ("bf16 A,B ~ U(-1,1) from Philox seed 0xB200") ---------------------
+ * Philox4x32-10, restated from Salmon, Moraes, Dror, Shaw, "Parallel random numbers: as easy as 1, 2, 3" (SC'11):
+ * ten rounds of  (hi0,lo0) = M0*c0, (hi1,lo1) = M1*c2,  c' = (hi1^c1^k0, lo1, hi0^c3^k1, lo0),  key += (W0, W1). */
+void oracle_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]) {
+    static const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+    uint32_t c[4] = {ctr[0], ctr[1], ctr[2], ctr[3]}, k[2] = {key[0], key[1]};
+    for (int round = 0; round < 10; ++round) {
+        uint64_t a = (uint64_t)M0 * c[0], b = (uint64_t)M1 * c[2];
+        uint32_t hi0 = (uint32_t)(a >> 32), lo0 = (uint32_t)a, hi1 = (uint32_t)(b >> 32), lo1 = (uint32_t)b;
+        uint32_t n[4] = {hi1 ^ c[1] ^ k[0], lo1, hi0 ^ c[3] ^ k[1], lo0};
+        memcpy(c, n, sizeof c);
+        k[0] += W0; k[1] += W1;
+    }
+    memcpy(out, c, sizeof c);
+}
+
+/* element e of matrix `which` (0 = A, 1 = B): word e mod 4 of block (e div 4, which, 0) under key (seed, 0); the top 24
+ * bits u give x = u / 2^23 - 1 in [-1, 1), then one round-to-nearest-even to bf16. */
+uint16_t oracle_gemm_uniform_bits(uint64_t e, uint32_t seed, int which) {
+    uint64_t blk = e / 4;
+    uint32_t ctr[4] = {(uint32_t)(blk & 0xffffffffu), (uint32_t)(blk >> 32), (uint32_t)which, 0u}, key[2] = {seed, 0u}, r[4];
+    oracle_philox4x32_10(ctr, key, r);
+    double x = (double)(r[e % 4] >> 8) / 8388608.0 - 1.0;     /* exact in fp64 and in fp32 */
+    return oracle_bf16_rne((float)x);
+}
+
+static double bf16_value(uint16_t bits) {
+    uint32_t u = (uint32_t)bits << 16;
+    float f;
+    memcpy(&f, &u, 4);
+    return (double)f;
+}
+
+double oracle_gemm_uniform_elem(uint64_t e, uint32_t seed, int which) { return bf16_value(oracle_gemm_uniform_bits(e, seed, which)); }
+
+double oracle_gemm_uniform_dot(int kdim, uint32_t seed, int row, int col) {
+    double acc = 0.0;
+    for (int k = 0; k < kdim; ++k)
+        acc += oracle_gemm_uniform_elem((uint64_t)row * kdim + k, seed, 0) * oracle_gemm_uniform_elem((uint64_t)col * kdim + k, seed, 1);
+    return acc;
+}
+
+/* tolerance of one output of the UNIFORM class: half a bf16 ulp of the reference (the final rounding, unit roundoff
+ * 2^-8) plus an fp32-accumulation allowance 2^-10 sqrt(K).  Inside SURVEY.md §8d's "2^-7 sqrt(K)-scaled" bound:
+ * at the typical output magnitude sqrt(K)/3 the two terms add up to (2^-8/3 + 2^-10) sqrt(K) < 2^-7 sqrt(K)/3. */
+double oracle_gemm_uniform_tol(int kdim, double ref) { return ldexp(fabs(ref), -8) + ldexp(sqrt((double)kdim), -10); }

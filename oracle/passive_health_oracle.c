@@ -25,6 +25,8 @@
 #include <ctype.h>
 #include <dlfcn.h>
 #include <nvml.h>
+#include <pthread.h>
+#include <sched.h>
 #include <stdint.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -190,4 +192,57 @@ double oracle_ph_time_poll(int iters, int timeout_ms) {
     double t0 = now_us();
     for (int i = 0; i < iters; ++i) oracle_ph_poll(timeout_ms);
     return (now_us() - t0) / iters;
+}
+
+/* SURVEY.md §8d config 1, N-thread variant: one thread per GPU (up to `threads`), each with its OWN event set registered
+ * on its device, `iters` zero-timeout waits after 10 warm-ups.  Returns the mean microseconds per poll seen by a thread;
+ * *polls_per_s = aggregate polls per second over all threads (wall clock of the slowest thread). */
+typedef struct { int dev, iters; double us; int rc; } poll_thread_t;
+static void* poll_thread(void* arg) {
+    poll_thread_t* t = (poll_thread_t*)arg;
+    nvmlEventSet_t set;
+    t->rc = -1;
+    if (pSetCreate(&set) != NVML_SUCCESS) return NULL;
+    unsigned long long sup = 0;
+    const unsigned long long want = nvmlEventTypeXidCriticalError | nvmlEventTypeDoubleBitEccError | nvmlEventTypeSingleBitEccError;
+    if (pSupported(H[t->dev], &sup) == NVML_SUCCESS && pRegister(H[t->dev], want & sup, set) == NVML_SUCCESS) {
+        nvmlEventData_t e;
+        for (int i = 0; i < 10; ++i) pSetWait(set, &e, 0);
+        double t0 = now_us();
+        for (int i = 0; i < t->iters; ++i) pSetWait(set, &e, 0);
+        t->us = (now_us() - t0) / t->iters;
+        t->rc = 0;
+    }
+    pSetFree(set);
+    return NULL;
+}
+double oracle_ph_time_poll_threads(int threads, int iters, double* polls_per_s) {
+    if (!L || N <= 0) return -1.0;
+    if (threads > N) threads = N;
+    if (threads < 1) threads = 1;
+    poll_thread_t t[ORACLE_MAXD];
+    pthread_t th[ORACLE_MAXD];
+    double t0 = now_us();
+    for (int i = 0; i < threads; ++i) { t[i].dev = i; t[i].iters = iters; t[i].us = 0; pthread_create(&th[i], NULL, poll_thread, &t[i]); }
+    double sum = 0;
+    for (int i = 0; i < threads; ++i) { pthread_join(th[i], NULL); if (t[i].rc) return -2.0; sum += t[i].us; }
+    double wall_us = now_us() - t0;
+    if (polls_per_s) *polls_per_s = (double)threads * (iters + 10) / (wall_us * 1e-6);
+    return sum / threads;
+}
+
+/* pin the calling thread to one CPU of its allowed set (the single-thread figures are quoted pinned); returns the CPU or -1 */
+int oracle_pin_self(int nth_allowed_cpu) {
+    cpu_set_t allowed, one;
+    if (sched_getaffinity(0, sizeof(allowed), &allowed)) return -1;
+    int seen = 0;
+    for (int c = 0; c < CPU_SETSIZE; ++c) {
+        if (!CPU_ISSET(c, &allowed)) continue;
+        if (seen++ == nth_allowed_cpu) {
+            CPU_ZERO(&one);
+            CPU_SET(c, &one);
+            return pthread_setaffinity_np(pthread_self(), sizeof(one), &one) ? -1 : c;
+        }
+    }
+    return -1;
 }

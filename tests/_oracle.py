@@ -23,6 +23,12 @@ def load():
     o.oracle_verify.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint32, u64p, u64p]
     o.oracle_host_sweep.restype = C.c_double
     o.oracle_host_sweep.argtypes = [C.c_uint64, C.c_int, C.c_int, C.c_int, C.c_uint32, u64p, u32p]
+    o.oracle_host_sweep_pinned.restype = C.c_double
+    o.oracle_host_sweep_pinned.argtypes = [C.c_uint64, C.c_int, C.c_int, C.c_int, C.c_uint32, u64p, u32p]
+    o.oracle_allowed_cpus.restype = C.c_int
+    o.oracle_ph_time_poll_threads.restype = C.c_double
+    o.oracle_ph_time_poll_threads.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_double)]
+    o.oracle_pin_self.argtypes = [C.c_int]
     o.oracle_a2a_chunk_seed.restype = C.c_uint32
     o.oracle_a2a_chunk_seed.argtypes = [C.c_uint32, C.c_int, C.c_int]
     o.oracle_gemm_elem.restype = C.c_double
@@ -33,6 +39,15 @@ def load():
     o.oracle_gemm_dot.argtypes = [C.c_int, C.c_uint32, C.c_int, C.c_int]
     o.oracle_bf16_rne.restype = C.c_uint16
     o.oracle_bf16_rne.argtypes = [C.c_float]
+    o.oracle_philox4x32_10.argtypes = [C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
+    o.oracle_gemm_uniform_bits.restype = C.c_uint16
+    o.oracle_gemm_uniform_bits.argtypes = [C.c_uint64, C.c_uint32, C.c_int]
+    o.oracle_gemm_uniform_elem.restype = C.c_double
+    o.oracle_gemm_uniform_elem.argtypes = [C.c_uint64, C.c_uint32, C.c_int]
+    o.oracle_gemm_uniform_dot.restype = C.c_double
+    o.oracle_gemm_uniform_dot.argtypes = [C.c_int, C.c_uint32, C.c_int, C.c_int]
+    o.oracle_gemm_uniform_tol.restype = C.c_double
+    o.oracle_gemm_uniform_tol.argtypes = [C.c_int, C.c_double]
     o.oracle_ph_open.argtypes = [C.c_char_p, C.c_char_p]
     o.oracle_ph_poll.argtypes = [C.c_int]
     o.oracle_ph_verdicts.argtypes = [C.POINTER(Verdict), C.c_int, C.POINTER(C.c_int)]
@@ -41,6 +56,12 @@ def load():
     o.oracle_ph_time_poll.restype = C.c_double
     o.oracle_ph_time_poll.argtypes = [C.c_int, C.c_int]
     return o
+
+
+def philox(o, ctr, key):
+    c, k, out = (C.c_uint32 * 4)(*ctr), (C.c_uint32 * 2)(*key), (C.c_uint32 * 4)()
+    o.oracle_philox4x32_10(c, k, out)
+    return list(out)
 
 
 def pattern_checksum(o, words, seed):

@@ -53,6 +53,35 @@ def bf16_rne(f):
     return ((u + r) >> 16) & 0xFFFF
 
 
+# Known-answer vectors of Philox4x32-10 as published with Random123 (kat_vectors: "philox4x32 10 ctr key -> out").
+# These are the one EXTERNAL pin of this fixture: the generator below is checked against them before it is used.
+PHILOX_KAT = [
+    ([0, 0, 0, 0], [0, 0], [0x6627E8D5, 0xE169C58D, 0xBC57AC4C, 0x9B00DBD8]),
+    ([M32, M32, M32, M32], [M32, M32], [0x408F276D, 0x41C83B0E, 0xA20BC7C6, 0x6D5451FD]),
+    ([0x243F6A88, 0x85A308D3, 0x13198A2E, 0x03707344], [0xA4093822, 0x299F31D0], [0xD16CFE09, 0x94FDCCEB, 0x5001E420, 0x24126EA1]),
+]
+
+
+def philox4x32_10(ctr, key):
+    c, k = list(ctr), list(key)
+    for _ in range(10):
+        p0, p1 = 0xD2511F53 * c[0], 0xCD9E8D57 * c[2]
+        c = [(p1 >> 32) ^ c[1] ^ k[0], p1 & M32, (p0 >> 32) ^ c[3] ^ k[1], p0 & M32]
+        k = [(k[0] + 0x9E3779B9) & M32, (k[1] + 0xBB67AE85) & M32]
+    return c
+
+
+def uniform_bits(e, seed, which):
+    """SURVEY.md §8d GEMM probe operands: bf16 U(-1,1) from Philox under key (seed, 0)."""
+    r = philox4x32_10([(e // 4) & M32, (e // 4) >> 32, which, 0], [seed, 0])[e % 4]
+    x = (r >> 8) / 8388608.0 - 1.0                      # exact
+    return bf16_rne(x)
+
+
+def bf16_value(bits):
+    return struct.unpack("<f", struct.pack("<I", bits << 16))[0]
+
+
 def checksum(words, seed):
     i = np.arange(words, dtype=np.uint64)
     w = ((i & np.uint64(M32)) * np.uint64(2654435761)) & np.uint64(M32)
@@ -64,7 +93,19 @@ def checksum(words, seed):
 
 
 def main():
-    g = {"reference_inputs": {}, "pattern": [], "checksum": [], "a2a_seed": [], "gemm_elem": [], "gemm_dot": [], "bf16_rne": []}
+    g = {"reference_inputs": {}, "pattern": [], "checksum": [], "a2a_seed": [], "gemm_elem": [], "gemm_dot": [], "bf16_rne": [],
+         "philox_kat": [], "gemm_uniform_elem": [], "gemm_uniform_dot": []}
+    for ctr, key, out in PHILOX_KAT:
+        assert philox4x32_10(ctr, key) == out, "the generator's Philox does not reproduce the Random123 known-answer vectors"
+        g["philox_kat"].append([ctr, key, out])
+    for which in (0, 1):
+        for e in list(range(12)) + [8191, 8192, 2**26 - 1, 2**34 + 6]:
+            g["gemm_uniform_elem"].append([e, 0xB200, which, uniform_bits(e, 0xB200, which)])
+    for kdim, row, col in ((64, 0, 0), (64, 1, 2), (256, 127, 255), (2048, 2047, 1), (8192, 4095, 8191)):
+        acc = 0.0
+        for k in range(kdim):                             # fp64 accumulate, in k order (what oracle_gemm_uniform_dot does)
+            acc += bf16_value(uniform_bits(row * kdim + k, 0xB200, 0)) * bf16_value(uniform_bits(col * kdim + k, 0xB200, 1))
+        g["gemm_uniform_dot"].append([kdim, row, col, acc])
     for name in ("values.yaml", "nvidia-smi.yaml", "jellyfin.yaml"):
         with open(os.path.join(REF, name), "rb") as f:
             raw = f.read()

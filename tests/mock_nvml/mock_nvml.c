@@ -11,6 +11,8 @@
  *   MOCK_NVML_EVENTS_QUERY_FAIL=i  nvmlDeviceGetSupportedEventTypes -> UNKNOWN for these
  *   MOCK_NVML_UUID_FAIL=i          nvmlDeviceGetUUID fails for these (enumeration error path)
  *   MOCK_NVML_LINKS_DOWN=d:l,d:l   link l of device d reports NVML_FEATURE_DISABLED
+ *   MOCK_NVML_BUSY=d:procs:util,.. device d reports `procs` foreign compute processes (pids 40000+) and `util` % GPU
+ *                                  utilisation (read at every query, so a test can change it between probe rounds)
  *   MOCK_NVML_EVENT_FILE=path      events for a mock living in ANOTHER process (the native daemon): every
  *                                  wait first queues the lines "kind dev data" appended to the file since
  *                                  the last wait
@@ -126,6 +128,30 @@ nvmlReturn_t nvmlDeviceGetSupportedEventTypes(nvmlDevice_t d, unsigned long long
     int i = ((mdev_t*)d)->idx;
     if (i < MAXD && g_query_fail[i]) return NVML_ERROR_UNKNOWN;
     *t = 0xff9fULL;      /* what a B200 on driver 580 reports (profiles/box_probe_r01.txt) */
+    return NVML_SUCCESS;
+}
+static void busy_of(int dev, int* procs, int* util) {
+    *procs = 0; *util = 0;
+    const char* s = getenv("MOCK_NVML_BUSY");
+    while (s && *s) {
+        int d = -1, p = 0, u = 0;
+        if (sscanf(s, "%d:%d:%d", &d, &p, &u) >= 2 && d == dev) { *procs = p; *util = u; }
+        s = strchr(s, ',');
+        if (s) ++s;
+    }
+}
+nvmlReturn_t nvmlDeviceGetComputeRunningProcesses_v3(nvmlDevice_t d, unsigned int* count, nvmlProcessInfo_t* infos) {
+    int procs, util;
+    busy_of(((mdev_t*)d)->idx, &procs, &util);
+    if (*count < (unsigned)procs) { *count = (unsigned)procs; return NVML_ERROR_INSUFFICIENT_SIZE; }
+    for (int i = 0; i < procs; ++i) { memset(&infos[i], 0, sizeof(infos[i])); infos[i].pid = 40000u + (unsigned)i; infos[i].usedGpuMemory = 1ull << 30; }
+    *count = (unsigned)procs;
+    return NVML_SUCCESS;
+}
+nvmlReturn_t nvmlDeviceGetUtilizationRates(nvmlDevice_t d, nvmlUtilization_t* u) {
+    int procs, util;
+    busy_of(((mdev_t*)d)->idx, &procs, &util);
+    u->gpu = (unsigned)util; u->memory = (unsigned)(util / 2);
     return NVML_SUCCESS;
 }
 nvmlReturn_t nvmlEventSetCreate(nvmlEventSet_t* s) { *s = (nvmlEventSet_t)&g_q; return NVML_SUCCESS; }

@@ -29,6 +29,7 @@ WORKER = textwrap.dedent("""
     shards = [list(D.shard_units(11, r, 2)) for r in range(2)]
     assert sorted(shards[0] + shards[1]) == list(range(11)) and len(shards[0]) == 6
     D.barrier()
+    D.host_barrier()          # on gloo: the plain barrier; on nccl: a CPU-side group, so waiting ranks leave their GPUs idle
     print("rank", rank, "ok")
 """) % ROOT
 

@@ -20,7 +20,9 @@ def env():
 
     if torch.cuda.device_count() < 2:
         pytest.skip("needs >= 2 GPUs")
-    return torch, Probe(), _oracle.load()
+    p = Probe()
+    yield torch, p, _oracle.load()
+    p.a2a_release()                  # the exchange context is resident between calls: hand the windows back
 
 
 VARIANTS = {0: "auto", 1: "pull-tma", 2: "push-tma", 3: "push-direct", 4: "push-buf", 5: "mix-tma", 6: "push-stagger", 7: "push-sync"}
@@ -58,7 +60,7 @@ def test_exchange_lands_oracle_pattern_in_every_recv_slot(env, S, variant):
     for dst in range(g):
         host = wins[dst].cpu().numpy()
         assert (host[2 * g * S + SYNC:] == 0x5A).all(), "wrote past the window"
-        assert not host[2 * g * S + 72 + 8 * 17 + 16:2 * g * S + SYNC].any(), "sync page: only flag[16], cnt, epoch, step_ns[17], done_cnt, end_ns may change"
+        assert not host[2 * g * S + 72 + 8 * 16 * 2 + 8:2 * g * S + SYNC].any(), "sync page: only flag[16], cnt, epoch, start_ns[16], done_ns[16], done_cnt may change"
         for src in range(g):
             want = _oracle.pattern(o, 0, S // 4, o.oracle_a2a_chunk_seed(SEED, src, dst))
             got = host[src * S:(src + 1) * S].view(np.uint32)
@@ -119,35 +121,70 @@ def test_only_peer_selectors(env):
 
 
 @pytest.mark.parametrize("variant", sorted(VARIANTS), ids=lambda v: VARIANTS[v])
-@pytest.mark.parametrize("mode", [0, 1, 2], ids=["peer-all", "peer-pair", "nccl"])
+@pytest.mark.parametrize("mode", [0, 1, 2, 3], ids=["peer-all", "peer-pair", "nccl", "copy-engines"])
 def test_single_process_probe_verifies_and_reports(env, mode, variant):
     torch, p, o = env
     g = min(torch.cuda.device_count(), 8)
+    if mode in (2, 3) and variant != 0:
+        pytest.skip("the library legs have no kernel variant")
     rep = p.nvlink_a2a(list(range(g)), bytes_per_pair=8 << 20, mode=mode, warmup=1, reps=3, verify=1, variant=variant)
     assert rep.verified == 1 and rep.g == g
+    assert rep.max_pair_gbs <= 900.0, "no pair can move faster than the 18 x 50 GB/s port"
     for i in range(g):
         for j in range(g):
             assert (rep.pair_gbs[i][j] > 0) == (i != j)
     if mode != 1:
         assert all(x > 0 for x in rep.egress_gbs) and all(x > 0 for x in rep.ingress_gbs) and rep.ms_median > 0
-    if mode == 0 and variant == 7 and g > 1:
-        # PUSH_SYNC stamps its steps: each pair's rate is its own (one pair per step), not the egress share,
-        # and the steps of one rank add up to its exchange
+    from k3s_nvidia_b200 import _lib as L
+    assert rep.pair_source == (L.PAIR_ISOLATED if mode == 1 else L.PAIR_STEPPED if (mode == 0 and variant == 7 and g > 2) else L.PAIR_SHARE)
+    if rep.pair_source == L.PAIR_STEPPED:
+        # PUSH_SYNC, drained and stamped steps: each pair's rate is its own (one pair per step, first byte issued to last
+        # store complete), not the egress share; the drained steps of one rank cannot be shorter than its free-running exchange
         for i in range(g):
             row = [rep.pair_gbs[i][j] for j in range(g) if j != i]
-            assert min(row) > 1.5 * rep.egress_gbs[i] / max(g - 1, 2) or g == 2
+            assert min(row) > 1.5 * rep.egress_gbs[i] / (g - 1)
             total_ms = sum((8 << 20) / (x * 1e6) for x in row)
-            assert 0.3 * rep.ms_median < total_ms < 1.5 * rep.ms_median
+            assert 0.3 * rep.ms_median < total_ms < 3.0 * rep.ms_median
 
 
 def test_full_size_exchange_properties(env):
-    """BASELINE config 3 at S = 256 MiB: library-verified landing of all G*(G-1) chunks, and the
-    egress figure is stable run to run within 5% (north_star asks 1% for fp results; link timing
-    is noisier, so the bound tested here is looser and the measured spread is reported in bench)."""
+    """BASELINE config 3 at S = 256 MiB through the plugin-facing entry: library-verified landing of all G*(G-1) chunks;
+    no cell of the pair matrix above the 900 GB/s port and the matrix flat within 5 % (through NVSwitch every pair sees the
+    same bandwidth: a cold cell is the fault signal, so a healthy box must read flat); egress stable run to run within 1 %
+    (north_star's bound; test_gpu_stability.py takes ten repeats); an absolute floor at 0.9 x the published figure."""
     torch, p, o = env
     g = min(torch.cuda.device_count(), 8)
     a = p.nvlink_a2a(list(range(g)), bytes_per_pair=256 << 20, warmup=2, reps=5, verify=1)
     b = p.nvlink_a2a(list(range(g)), bytes_per_pair=256 << 20, warmup=2, reps=5, verify=1)
     assert a.verified == 1 and b.verified == 1
-    for x, y in zip(a.ingress_gbs[:g], b.ingress_gbs[:g]):
-        assert abs(x - y) / max(x, y) < 0.05
+    for x, y in zip(a.egress_gbs[:g], b.egress_gbs[:g]):
+        assert abs(x - y) / max(x, y) < 0.01
+    for rep in (a, b):
+        assert rep.max_pair_gbs <= 900.0
+        assert rep.max_pair_gbs / rep.min_pair_gbs <= 1.05
+        assert min(rep.egress_gbs[:g]) >= 0.9 * (692.0 if g == 2 else 700.0)      # DESIGN.md §5: 692 at G = 2, 700 at G = 8
+
+
+def test_resident_context_and_release(env):
+    """Windows, streams and communicators stay resident between calls with the same key (a probe round calls the entry
+    several times); a different size replaces them; release frees them; the data result does not depend on any of it."""
+    import time
+
+    torch, p, o = env
+    g = min(torch.cuda.device_count(), 8)
+    p.a2a_release()
+    free0 = torch.cuda.mem_get_info(0)[0]
+    S = 64 << 20
+    t0 = time.perf_counter()
+    a = p.nvlink_a2a(list(range(g)), bytes_per_pair=S, warmup=1, reps=2, verify=1)
+    t_first = time.perf_counter() - t0
+    held = free0 - torch.cuda.mem_get_info(0)[0]
+    assert held >= 2 * g * S                                   # the window is still there
+    t0 = time.perf_counter()
+    b = p.nvlink_a2a(list(range(g)), bytes_per_pair=S, warmup=1, reps=2, verify=1)
+    t_second = time.perf_counter() - t0
+    assert a.verified == 1 and b.verified == 1 and t_second <= t_first
+    c = p.nvlink_a2a(list(range(g)), bytes_per_pair=S // 2, warmup=1, reps=2, verify=1)      # new key: the old context is replaced
+    assert c.verified == 1 and free0 - torch.cuda.mem_get_info(0)[0] < held
+    p.a2a_release()
+    assert free0 - torch.cuda.mem_get_info(0)[0] < (64 << 20)

@@ -898,7 +898,36 @@ def test_probe_round_without_a_gpu_publishes_unhealthy_like_the_python_runner(tm
         py = L.ActiveProbeRunner(p, features_dir=str(tmp_path / "py"), interval_s=3600).run_once()
     finally:
         p.close()
-    native.pop("nvidia.com/b200probe.timestamp")
-    py.pop("nvidia.com/b200probe.timestamp")
+    assert "nvidia.com/b200probe.timestamp" not in native        # no churning label: staleness is the file's expiry directive
+    assert out.stdout.count("# +expiry-time=") == 0 and open(tmp_path / "native" / "b200probe").read().startswith("# +expiry-time=")
     assert native == py
     assert native["nvidia.com/b200probe.healthy"] == "false" and native["nvidia.com/b200probe.gpu1.nvlink-links-ok"] == "false"
+
+
+def test_both_hosts_skip_a_busy_gpu_the_same_way(tmp_path, monkeypatch):
+    """A GPU with a foreign compute process (mock NVML) is not probed by either host: probe-state=busy, no verdict label
+    for it (nothing to carry over on a first round), while the idle GPU's probe is attempted (and fails here: no CUDA)."""
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from k3s_nvidia_b200 import labels as L
+    from k3s_nvidia_b200.probe import Probe
+
+    env = dict(os.environ, MOCK_NVML_DEVICES="2", MOCK_NVML_BUSY="1:1:0")
+    out = subprocess.run([BIN, "--probe-once", "--features-dir", str(tmp_path / "native"), "--nvml-path", _oracle.MOCK_NVML], env=env,
+                         capture_output=True, text=True, timeout=60)
+    assert out.returncode == 0, out.stderr
+    native = L.parse_feature_file(out.stdout)
+    monkeypatch.setenv("MOCK_NVML_DEVICES", "2")
+    monkeypatch.setenv("MOCK_NVML_BUSY", "1:1:0")
+    p = Probe(_oracle.MOCK_NVML)
+    try:
+        py = L.ActiveProbeRunner(p, features_dir=str(tmp_path / "py"), interval_s=3600).run_once()
+    finally:
+        p.close()
+    assert native == py
+    P = "nvidia.com/b200probe."
+    assert native[P + "gpu1.probe-state"] == "busy" and native[P + "gpu0.probe-state"] == "probed"
+    assert P + "gpu1.hbm-healthy" not in native and native[P + "gpu0.hbm-healthy"] == "false"
+    assert P + "nvlink-healthy" not in native                   # fewer than two idle GPUs: no exchange, no NVLink verdict

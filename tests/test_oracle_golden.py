@@ -65,6 +65,38 @@ def test_gemm_elements_and_dots(o):
         assert o.oracle_bf16_rne(got) == bits
 
 
+def test_philox_known_answer_vectors(o):
+    """The one externally published pin of this oracle: Random123's Philox4x32-10 known-answer vectors."""
+    assert len(G["philox_kat"]) == 3
+    for ctr, key, out in G["philox_kat"]:
+        assert _oracle.philox(o, ctr, key) == out
+
+
+def test_gemm_uniform_operands_and_dots(o):
+    for e, seed, which, bits in G["gemm_uniform_elem"]:
+        assert o.oracle_gemm_uniform_bits(e, seed, which) == bits
+        v = o.oracle_gemm_uniform_elem(e, seed, which)
+        assert -1.0 <= v <= 1.0
+    for kdim, row, col, acc in G["gemm_uniform_dot"]:
+        assert o.oracle_gemm_uniform_dot(kdim, 0xB200, row, col) == acc      # same fp64 sum in the same order: bit-identical
+    # the class really is U(-1,1): mean ~ 0, variance ~ 1/3 over 64 Ki elements
+    v = np.array([o.oracle_gemm_uniform_elem(e, 0xB200, 0) for e in range(1 << 16)])
+    assert abs(v.mean()) < 0.01 and abs(v.var() - 1.0 / 3.0) < 0.01
+    assert o.oracle_gemm_uniform_tol(8192, 30.0) == 30.0 / 256 + 8192 ** 0.5 / 1024
+
+
+def test_product_operand_generator_matches_oracle():
+    """The library's host-side element function (what its own check multiplies) against the oracle, both classes.
+    No GPU needed: b200probe_gemm_operand_bits is plain host code."""
+    from k3s_nvidia_b200 import _lib
+
+    lib, o = _lib.load(), _oracle.load()
+    for e in list(range(64)) + [8191, 8192, 2**26 - 1, 2**34 + 6]:
+        for m in (0, 1):
+            assert lib.b200probe_gemm_operand_bits(e, 0xB200, m) == o.oracle_gemm_elem_bits(e, 0xB200, m)
+            assert lib.b200probe_gemm_operand_bits(e, 0xB200, m | 2) == o.oracle_gemm_uniform_bits(e, 0xB200, m)
+
+
 def test_bf16_rne(o):
     for f, bits in G["bf16_rne"]:
         assert o.oracle_bf16_rne(f) == bits

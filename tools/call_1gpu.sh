@@ -1,7 +1,10 @@
 #!/bin/bash
+# round 2, 1-GPU validation + HBM evidence: GPU tests, policy/map/phase experiments on the copy kernel, DRAM counters per mode
 mkdir -p gpurun_out
-python -m pytest tests -m gpu -x -q 2>&1 | tail -5 | tee gpurun_out/pytest_gpu_1.txt
-python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2
-python bench.py --steps 500 --warmup 20 > gpurun_out/bench_n1.json 2> gpurun_out/bench_n1.err; python -c "
-import json; s=open('gpurun_out/bench_n1.json').read().strip().splitlines(); print(len(s),'line(s)'); d=json.loads(s[-1]); print(d['value'], d['roofline']['frac'], d['e2e'], d['e2e_hostbuf']['value'], d['hbm_read_gbs'], d['hbm_write_gbs'])"; tail -3 gpurun_out/bench_n1.err
-python bench.py --impl reference --steps 20 --warmup 3 2>/dev/null | head -c 400
+export CUDA_VISIBLE_DEVICES=0
+( time timeout 1200 python -m pytest tests -m gpu -x -q ) > gpurun_out/pytest_gpu_1gpu.log 2>&1; tail -5 gpurun_out/pytest_gpu_1gpu.log
+timeout 600 python tools/hbm_evidence.py > gpurun_out/hbm_evidence.log 2>&1; tail -3 gpurun_out/hbm_evidence.log
+M=gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,dram__cycles_elapsed.avg,dram__cycles_active.avg,dram__cycles_active_read.avg,dram__cycles_active_write.avg,dram__throughput.avg.pct_of_peak_sustained_elapsed,fbpa__dram_read_throughput.avg.pct_of_peak_sustained_elapsed,fbpa__dram_write_throughput.avg.pct_of_peak_sustained_elapsed,lts__throughput.avg.pct_of_peak_sustained_elapsed,lts__t_sectors_op_read.sum,lts__t_sectors_op_write.sum,lts__t_sector_hit_rate.pct,dram__cycles_elapsed.avg.per_second
+timeout 600 ncu --metrics $M --clock-control none -k regex:'hbm_ring_kernel' -c 4 --csv --log-file gpurun_out/ncu_hbm_dram_counters.csv python tools/prof_hbm.py > gpurun_out/prof_hbm.log 2>&1
+tail -2 gpurun_out/prof_hbm.log
+nvidia-smi --query-gpu=name,clocks.max.sm,clocks.max.mem,power.limit --format=csv
