@@ -99,9 +99,14 @@ __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&v)[32])
         : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src_smem, int c0, int c1) {
-    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"((uint64_t)map), "r"(src_smem), "r"(c0), "r"(c1)
-                 : "memory");
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src_smem, int c0, int c1, uint64_t pol = 0) {
+    if (pol)
+        asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group.L2::cache_hint [%0, {%2, %3}], [%1], %4;" ::"l"((uint64_t)map), "r"(src_smem), "r"(c0),
+                     "r"(c1), "l"(pol)
+                     : "memory");
+    else
+        asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"((uint64_t)map), "r"(src_smem), "r"(c0), "r"(c1)
+                     : "memory");
 }
 __device__ __forceinline__ void bulk_commit_group() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
@@ -131,7 +136,7 @@ __device__ __forceinline__ void pack_half_row(const uint32_t (&v)[32], uint8_t* 
 // to the MMA issuer as soon as the last tcgen05.ld has landed, before the stores finish.
 template <class Release>
 __device__ __forceinline__ void epilogue_slice(uint32_t taddr, uint8_t* stage, uint32_t& ubuf, const CUtensorMap* tmc, int row0, int col0, int lane,
-                                               Release release) {
+                                               Release release, uint64_t polc = 0) {
     uint32_t va[32], vb[32];
     tmem_ld_32x32(taddr, va);
     tmem_ld_wait();
@@ -149,7 +154,7 @@ __device__ __forceinline__ void epilogue_slice(uint32_t taddr, uint8_t* stage, u
         fence_async_smem();
         __syncwarp();
         if (lane == 0) {
-            tma_store_2d(tmc, smem_u32(buf), col0 + u * EPI_UNIT_COLS, row0);
+            tma_store_2d(tmc, smem_u32(buf), col0 + u * EPI_UNIT_COLS, row0, polc);
             bulk_commit_group();
         }
         ubuf ^= 1;
@@ -311,6 +316,29 @@ __device__ __forceinline__ void umma_commit_2sm(uint32_t bar) {
 __device__ __forceinline__ void mbar_arrive_leader(uint32_t bar) {
     asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar & kPeerBitMask) : "memory");
 }
+// tuning knobs of the CTA-pair kernel (environment, experiments only; defaults = the shipped schedule)
+struct GemmTune {
+    int group_m;            // m-tiles (of 256 rows) per rasterisation band
+    int pol_a, pol_b;       // L2 eviction policy of the A / B tensor loads: 0 none, 1 evict_first, 2 evict_last
+    int pol_c;              // ... and of the C tensor stores
+    int prefetch;           // 512 x 256 kernel: k-blocks by which an L2 prefetch of the operand boxes runs ahead of the loads (0 = none)
+    int expt;               // attribution experiments (WRONG results): 1 = the epilogue hands the accumulators back without reading them
+    int epi;                // 512 x 256 kernel epilogue: 0 = 32-byte stores from registers (default), 1 = staged tensor stores
+};
+__device__ __forceinline__ void tma_prefetch_l2_2d(const CUtensorMap* map, int c0, int c1) {
+    asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"((uint64_t)map), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ uint64_t l2_policy(int kind) {
+    uint64_t p = 0;
+    if (kind == 1) asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    else if (kind == 2) asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ void tma_load_2d_2sm_hint(uint32_t dst_smem, const CUtensorMap* map, uint32_t bar, int c0, int c1, uint64_t pol) {
+    asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4}], [%2], %5;" ::"r"(dst_smem),
+                 "l"((uint64_t)map), "r"(bar & 0xFEFFFFFFu), "r"(c0), "r"(c1), "l"(pol)
+                 : "memory");
+}
 constexpr int STAGES2 = 6;
 constexpr int A2_STAGE_BYTES = BM * BK * 2;             // this CTA's 128 rows of the 256-row A tile
 constexpr int B2_STAGE_BYTES = (BN / 2) * BK * 2;       // this CTA's 128 of the 256 B rows
@@ -319,11 +347,11 @@ constexpr int SMEM2_BYTES = STAGES2 * STAGE2_BYTES + EPI_BYTES + 1024 + 256;
 static_assert(SMEM2_BYTES <= 232448 && SMEM_BYTES <= 232448, "227 KiB of shared memory per CTA");
 constexpr uint32_t kIdesc2 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((2 * BM) >> 4) << 24);   // M = 256
 
-__device__ __forceinline__ TileCoord tile_coord2(int t, int num_m, int num_n) {     // tiles of (2*BM) x BN
-    const int per_band = (GROUP_M / 2) * num_n;
+__device__ __forceinline__ TileCoord tile_coord2(int t, int num_m, int num_n, int group) {     // tiles of (2*BM) x BN, `group` m-tiles per band
+    const int per_band = group * num_n;
     const int band = t / per_band;
-    const int first_m = band * (GROUP_M / 2);
-    const int rows = min(GROUP_M / 2, num_m - first_m);
+    const int first_m = band * group;
+    const int rows = min(group, num_m - first_m);
     const int in_band = t - band * per_band;
     return {(first_m + in_band % rows) * 2 * BM, (in_band / rows) * BN};
 }
@@ -333,7 +361,7 @@ __device__ __forceinline__ TileCoord tile_coord2(int t, int num_m, int num_n) { 
 // 1-CTA kernel), holds its 128 accumulator rows in its own TMEM and runs its own epilogue.
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
 gemm_bf16_tn_2cta_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, const __grid_constant__ CUtensorMap tma_c,
-                         int M, int N, int K) {
+                         int M, int N, int K, GemmTune tune) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     uint8_t* smem_a = smem;
@@ -374,15 +402,18 @@ gemm_bf16_tn_2cta_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid
     if (warp == 0) {
         if (lane == 0) {                                   // ===== TMA producer (both CTAs) =====
             uint32_t stage = 0, phase = 0;
+            const uint64_t pa = l2_policy(tune.pol_a), pb = l2_policy(tune.pol_b);
             for (int t = pair; t < num_tiles; t += num_pairs) {
-                const TileCoord tc = tile_coord2(t, num_m, num_n);
+                const TileCoord tc = tile_coord2(t, num_m, num_n, tune.group_m);
                 const int my_m = tc.m0 + (int)cta_rank * BM, my_n = tc.n0 + (int)cta_rank * (BN / 2);
                 for (int kb = 0; kb < num_kb; ++kb) {
                     mbar_wait(smem_u32(&empty[stage]), phase ^ 1);
                     const uint32_t fb = smem_u32(&full[stage]);
                     if (leader) mbar_expect_tx(fb, 2 * STAGE2_BYTES);      // both CTAs' bytes land on the leader's barrier
-                    tma_load_2d_2sm(smem_u32(smem_a + stage * A2_STAGE_BYTES), &tma_a, fb, kb * BK, my_m);
-                    tma_load_2d_2sm(smem_u32(smem_b + stage * B2_STAGE_BYTES), &tma_b, fb, kb * BK, my_n);
+                    if (tune.pol_a) tma_load_2d_2sm_hint(smem_u32(smem_a + stage * A2_STAGE_BYTES), &tma_a, fb, kb * BK, my_m, pa);
+                    else tma_load_2d_2sm(smem_u32(smem_a + stage * A2_STAGE_BYTES), &tma_a, fb, kb * BK, my_m);
+                    if (tune.pol_b) tma_load_2d_2sm_hint(smem_u32(smem_b + stage * B2_STAGE_BYTES), &tma_b, fb, kb * BK, my_n, pb);
+                    else tma_load_2d_2sm(smem_u32(smem_b + stage * B2_STAGE_BYTES), &tma_b, fb, kb * BK, my_n);
                     if (++stage == STAGES2) { stage = 0; phase ^= 1; }
                 }
             }
@@ -412,8 +443,9 @@ gemm_bf16_tn_2cta_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid
     } else if (warp >= 4) {                                // ===== epilogue (both CTAs, own 128 rows) =====
         const int q = warp - 4;
         uint32_t it = 0, ubuf = 0;
+        const uint64_t polc = l2_policy(tune.pol_c);
         for (int t = pair; t < num_tiles; t += num_pairs, ++it) {
-            const TileCoord tc = tile_coord2(t, num_m, num_n);
+            const TileCoord tc = tile_coord2(t, num_m, num_n, tune.group_m);
             const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
             mbar_wait(smem_u32(&tfull[acc]), acc_phase);
             tc_fence_after();
@@ -423,7 +455,257 @@ gemm_bf16_tn_2cta_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive_leader(tempty_bar);
-            });
+            }, polc);
+        }
+        if (lane == 0) bulk_wait_all0();
+    }
+    tc_fence_before();
+    cluster_sync_all();            // the peer's MMAs read this CTA's shared memory: nobody leaves early
+    if (warp == 2) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
+    }
+}
+
+// ---- epilogue in 32-column units (the 512 x 256 kernel: EIGHT epilogue warps, one 32-row x 256-column accumulator slice each) ----
+// One unit = one tcgen05.ld (32 lanes x 32 fp32 columns) -> 32 bf16 = a 64-byte row segment -> staging buffer in the SWIZZLE_64B
+// layout of the 32-column C map (16-byte chunk j of row r at chunk j ^ ((r >> 1) & 3): rows 64 B apart, conflict-free) -> one
+// tensor store of 32 rows x 64 B.  Two register sets and two 2 KiB buffers per warp: the next load and the previous store are in
+// flight while a unit is converted.  8 warps x 2 x 2 KiB = the same 32 KiB the 64-column path uses for 4 warps.
+constexpr int EPI32_BUF_BYTES = 32 * 32 * 2;      // 2 KiB
+__device__ __forceinline__ void pack_row32(const uint32_t (&v)[32], uint8_t* row, int lane) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        uint32_t pk[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            __nv_bfloat162 h = __floats2bfloat162_rn(__uint_as_float(v[8 * j + 2 * i]), __uint_as_float(v[8 * j + 2 * i + 1]));
+            pk[i] = *reinterpret_cast<uint32_t*>(&h);
+        }
+        *reinterpret_cast<uint4*>(row + ((j ^ ((lane >> 1) & 3)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+    }
+}
+template <class Release>
+__device__ __forceinline__ void epilogue_slice32(uint32_t taddr, uint8_t* stage, uint32_t& ubuf, const CUtensorMap* tmc32, int row0, int col0, int lane,
+                                                 Release release, uint64_t polc) {
+    uint32_t va[32], vb[32];
+    tmem_ld_32x32(taddr, va);
+    tmem_ld_wait();
+#pragma unroll
+    for (int u = 0; u < BN / 32; u += 2) {
+        // unit u from va while the load of unit u+1 is in flight
+        tmem_ld_32x32(taddr + (u + 1) * 32, vb);
+        if (lane == 0) bulk_wait_read1();
+        __syncwarp();
+        uint8_t* buf = stage + ubuf * EPI32_BUF_BYTES;
+        pack_row32(va, buf + lane * 64, lane);
+        fence_async_smem();
+        __syncwarp();
+        if (lane == 0) { tma_store_2d(tmc32, smem_u32(buf), col0 + u * 32, row0, polc); bulk_commit_group(); }
+        ubuf ^= 1;
+        tmem_ld_wait();
+        // unit u+1 from vb while the load of unit u+2 is in flight
+        if (u + 2 < BN / 32) tmem_ld_32x32(taddr + (u + 2) * 32, va);
+        else release();                                             // the whole slice is in registers
+        if (lane == 0) bulk_wait_read1();
+        __syncwarp();
+        buf = stage + ubuf * EPI32_BUF_BYTES;
+        pack_row32(vb, buf + lane * 64, lane);
+        fence_async_smem();
+        __syncwarp();
+        if (lane == 0) { tma_store_2d(tmc32, smem_u32(buf), col0 + (u + 1) * 32, row0, polc); bulk_commit_group(); }
+        ubuf ^= 1;
+        if (u + 2 < BN / 32) tmem_ld_wait();
+    }
+}
+
+// ---- epilogue straight from registers: 32 fp32 columns -> 32 bf16 = 64 bytes of one C row = TWO 32-byte stores per lane
+// (st.global.v8.b32, SASS STG.E.256: every store fills one whole 32-byte sector).  No staging buffer, no tensor store: at a tile
+// boundary the TMA unit is busy prefetching the next tile's four operand stages (192 KiB per CTA), and small tensor stores queued
+// behind those loads held the accumulators for about 3 us per tile (3.4 % of the step, measured by handing the accumulators back
+// unread: tools/gemm_tune.py expt 1); plain stores go through the LSU and retire independently.
+__device__ __forceinline__ void store_row32(const uint32_t (&v)[32], __nv_bfloat16* dst) {
+    uint32_t pk[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        __nv_bfloat162 h = __floats2bfloat162_rn(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1]));
+        pk[i] = *reinterpret_cast<uint32_t*>(&h);
+    }
+    asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(dst), "r"(pk[0]), "r"(pk[1]), "r"(pk[2]), "r"(pk[3]), "r"(pk[4]), "r"(pk[5]),
+                 "r"(pk[6]), "r"(pk[7])
+                 : "memory");
+    asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(dst + 16), "r"(pk[8]), "r"(pk[9]), "r"(pk[10]), "r"(pk[11]), "r"(pk[12]),
+                 "r"(pk[13]), "r"(pk[14]), "r"(pk[15])
+                 : "memory");
+}
+template <class Release>
+__device__ __forceinline__ void epilogue_slice_direct(uint32_t taddr, __nv_bfloat16* crow /* this lane's row, first column of the tile */, bool row_ok,
+                                                      Release release) {
+    uint32_t va[32], vb[32];
+    tmem_ld_32x32(taddr, va);
+    tmem_ld_wait();
+#pragma unroll
+    for (int u = 0; u < BN / 32; u += 2) {
+        tmem_ld_32x32(taddr + (u + 1) * 32, vb);                    // in flight while va is converted and stored
+        if (row_ok) store_row32(va, crow + u * 32);
+        tmem_ld_wait();
+        if (u + 2 < BN / 32) tmem_ld_32x32(taddr + (u + 2) * 32, va);
+        else release();                                             // the whole slice has left TMEM
+        if (row_ok) store_row32(vb, crow + (u + 1) * 32);
+        if (u + 2 < BN / 32) tmem_ld_wait();
+    }
+}
+
+// ---- 512 x 256 per CTA pair ---------------------------------------------------------------------------------------------
+// Each CTA of the pair stages 256 A rows (two 128-row halves) and 128 of the 256 B rows per k-block, and every k16 step issues
+// TWO cta_group::2 MMAs (M256 N256 K16) against the same B stage: half h of both CTAs' A -> accumulator h (TMEM columns
+// [256h, 256h+256)).  Per flop the shared-memory fill (and the L2 -> SM traffic behind it) is 3/4 of the 256 x 256 pair tile's:
+// 768 operand rows per 512 x 256 x 64 block instead of 512 per 256 x 256 x 64.  At the 1 kW power cap that is what decides the
+// clock: ncu had the 256 x 256 kernel at 47.9 % L2 throughput and 1.39 GHz next to cuBLAS's 512 x 256 kernel
+// (nvjet_tst_256x256_64x4_2x1_2cta) at 30.3 % and 1.48 GHz on the same operands (profiles/ncu_gemm_vs_cublas_r02.txt).
+// Price: both accumulators = all 512 TMEM columns, so a tile's epilogue is not hidden behind the next tile's MMAs; the kernel
+// stays persistent, so the next tile's TMA prologue (4 stages) does run under the epilogue.
+constexpr int STAGES3 = 4;
+constexpr int A3_STAGE_BYTES = 2 * BM * BK * 2;         // this CTA's 256 A rows: 32 KiB, rows [128, 256) start 16 KiB in
+constexpr int B3_STAGE_BYTES = (BN / 2) * BK * 2;       // this CTA's 128 of the 256 B rows: 16 KiB
+constexpr int STAGE3_BYTES = A3_STAGE_BYTES + B3_STAGE_BYTES;
+constexpr int SMEM3_BYTES = STAGES3 * STAGE3_BYTES + EPI_BYTES + 1024 + 256;
+static_assert(SMEM3_BYTES <= 232448, "227 KiB of shared memory per CTA");
+
+__device__ __forceinline__ TileCoord tile_coord3(int t, int num_m, int num_n, int group) {     // tiles of (4*BM) x BN
+    const int per_band = group * num_n;
+    const int band = t / per_band;
+    const int first_m = band * group;
+    const int rows = min(group, num_m - first_m);
+    const int in_band = t - band * per_band;
+    return {(first_m + in_band % rows) * 4 * BM, (in_band / rows) * BN};
+}
+
+constexpr int NUM_THREADS3 = 384;                       // warps 0-3: TMA producer, MMA issuer, TMEM allocator, idle; warps 4-11: epilogue
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS3, 1)
+gemm_bf16_tn_2cta_512_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, const __grid_constant__ CUtensorMap tma_c,
+                             __nv_bfloat16* __restrict__ C, int M, int N, int K, GemmTune tune) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint8_t* smem_a = smem;
+    uint8_t* smem_b = smem + STAGES3 * A3_STAGE_BYTES;
+    uint8_t* smem_epi = smem + STAGES3 * STAGE3_BYTES;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_epi + EPI_BYTES);
+    uint64_t* full = bars;                   // [STAGES3]  used in the leader only
+    uint64_t* empty = bars + STAGES3;        // [STAGES3]  one per CTA, signalled by multicast commit
+    uint64_t* tfull = bars + 2 * STAGES3;    // one per CTA, signalled by multicast commit: both accumulators of the tile are complete
+    uint64_t* tempty = tfull + 1;            // leader only: the 8 epilogue warps of the pair have both accumulators in registers
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t cta_rank = cluster_ctarank();
+    const bool leader = cta_rank == 0;
+    // rows past M are zero-filled by the tensor loads and clipped by the tensor stores: any M that is a multiple of 128 works
+    const int num_m = (M + 4 * BM - 1) / (4 * BM), num_n = N / BN, num_tiles = num_m * num_n, num_kb = K / BK;
+    const int pair = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tma_a) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tma_b) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tma_c) : "memory");
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < STAGES3; ++s) { mbar_init(smem_u32(&full[s]), 1); mbar_init(smem_u32(&empty[s]), 1); }
+        mbar_init(smem_u32(tfull), 1);
+        mbar_init(smem_u32(tempty), 16);                                   // 8 epilogue warps in each CTA of the pair
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {                                   // ===== TMA producer (both CTAs) =====
+            uint32_t stage = 0, phase = 0;
+            const uint64_t pa = l2_policy(tune.pol_a), pb = l2_policy(tune.pol_b);
+            // L2 prefetch `tune.prefetch` k-blocks ahead of the loads (across tile boundaries): about a quarter of the operand sectors
+            // miss L2, and with 48 KiB per stage nearly every stage holds a miss, so without it a stage's latency is DRAM's
+            auto prefetch_block = [&](long long gkb) {
+                const int ti = pair + (int)(gkb / num_kb) * num_pairs;
+                if (ti >= num_tiles) return;
+                const TileCoord pc = tile_coord3(ti, num_m, num_n, tune.group_m);
+                const int k0 = (int)(gkb % num_kb) * BK;
+                tma_prefetch_l2_2d(&tma_a, k0, pc.m0 + (int)cta_rank * 2 * BM);
+                tma_prefetch_l2_2d(&tma_b, k0, pc.n0 + (int)cta_rank * (BN / 2));
+            };
+            long long gkb = 0;
+            for (int pf = 0; pf < tune.prefetch; ++pf) prefetch_block(pf);
+            for (int t = pair; t < num_tiles; t += num_pairs) {
+                const TileCoord tc = tile_coord3(t, num_m, num_n, tune.group_m);
+                const int my_m = tc.m0 + (int)cta_rank * 2 * BM, my_n = tc.n0 + (int)cta_rank * (BN / 2);
+                for (int kb = 0; kb < num_kb; ++kb, ++gkb) {
+                    if (tune.prefetch) prefetch_block(gkb + tune.prefetch);
+                    mbar_wait(smem_u32(&empty[stage]), phase ^ 1);
+                    const uint32_t fb = smem_u32(&full[stage]);
+                    if (leader) mbar_expect_tx(fb, 2 * STAGE3_BYTES);      // both CTAs' bytes land on the leader's barrier
+                    if (tune.pol_a) tma_load_2d_2sm_hint(smem_u32(smem_a + stage * A3_STAGE_BYTES), &tma_a, fb, kb * BK, my_m, pa);
+                    else tma_load_2d_2sm(smem_u32(smem_a + stage * A3_STAGE_BYTES), &tma_a, fb, kb * BK, my_m);
+                    if (tune.pol_b) tma_load_2d_2sm_hint(smem_u32(smem_b + stage * B3_STAGE_BYTES), &tma_b, fb, kb * BK, my_n, pb);
+                    else tma_load_2d_2sm(smem_u32(smem_b + stage * B3_STAGE_BYTES), &tma_b, fb, kb * BK, my_n);
+                    if (++stage == STAGES3) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (leader && lane == 0) {                         // ===== MMA issuer (leader CTA only) =====
+            uint32_t stage = 0, phase = 0, it = 0;
+            for (int t = pair; t < num_tiles; t += num_pairs, ++it) {
+                mbar_wait(smem_u32(tempty), (it & 1) ^ 1);                 // the epilogue has drained the previous tile's accumulators
+                tc_fence_after();
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    mbar_wait(smem_u32(&full[stage]), phase);
+                    tc_fence_after();
+                    const uint64_t a_desc = make_smem_desc(smem_u32(smem_a + stage * A3_STAGE_BYTES));
+                    const uint64_t b_desc = make_smem_desc(smem_u32(smem_b + stage * B3_STAGE_BYTES));
+#pragma unroll
+                    for (int k = 0; k < BK / UMMA_K; ++k) {
+                        umma_bf16_2sm(tmem_base, a_desc + (uint64_t)(k * 2), b_desc + (uint64_t)(k * 2), kIdesc2, (kb | k) != 0);
+                        umma_bf16_2sm(tmem_base + BN, a_desc + (uint64_t)((BM * BK * 2) >> 4) + (uint64_t)(k * 2), b_desc + (uint64_t)(k * 2), kIdesc2, (kb | k) != 0);
+                    }
+                    umma_commit_2sm(smem_u32(&empty[stage]));
+                    if (++stage == STAGES3) { stage = 0; phase ^= 1; }
+                }
+                umma_commit_2sm(smem_u32(tfull));
+            }
+        }
+    } else if (warp >= 4) {                                // ===== epilogue (both CTAs): warp -> accumulator h, TMEM lane quadrant q =====
+        const int q = warp & 3, h = (warp - 4) >> 2;       // a warp may read TMEM lanes [32 (warp % 4), +32)
+        uint32_t it = 0, ubuf = 0;
+        const uint64_t polc = l2_policy(tune.pol_c);
+        const uint32_t tempty_bar = smem_u32(tempty);
+        uint8_t* const stage = smem_epi + (warp - 4) * 2 * EPI32_BUF_BYTES;
+        for (int t = pair; t < num_tiles; t += num_pairs, ++it) {
+            const TileCoord tc = tile_coord3(t, num_m, num_n, tune.group_m);
+            mbar_wait(smem_u32(tfull), it & 1);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + h * BN;
+            const int row0 = tc.m0 + (int)cta_rank * 2 * BM + h * BM + q * 32;
+            auto release = [&]() {
+                tc_fence_before();                         // this warp's slice is in registers: 16 such arrivals free both accumulators
+                __syncwarp();
+                if (lane == 0) mbar_arrive_leader(tempty_bar);
+            };
+            if (tune.expt == 1) { release(); continue; }   // how much of the step is the exposed epilogue?  (results are not written)
+            if (tune.epi == 0) {
+                const int row = row0 + lane;
+                epilogue_slice_direct(taddr, C + (size_t)row * N + tc.n0, row < M, release);
+                continue;
+            }
+            epilogue_slice32(taddr, stage, ubuf, &tma_c, row0, tc.n0, lane, [&]() {
+                tc_fence_before();                         // this warp's slice is in registers: 16 such arrivals free both accumulators
+                __syncwarp();
+                if (lane == 0) mbar_arrive_leader(tempty_bar);
+            }, polc);
         }
         if (lane == 0) bulk_wait_all0();
     }
@@ -485,16 +767,20 @@ int get_encode(EncodeTiledFn* fn) {
 }
 
 // [rows][inner] bf16 row-major -> box {64 (inner), box_rows}, 128B swizzle.  Operands: inner = K; C: inner = N.
-int make_map(CUtensorMap* map, const void* base, int rows, int inner, int box_rows) {
+// box_cols = 32 selects the 64-byte-swizzled map of the 32-column epilogue units.
+int make_map(CUtensorMap* map, const void* base, int rows, int inner, int box_rows, int box_cols = BK) {
     EncodeTiledFn enc = nullptr;
     int rc = get_encode(&enc);
     if (rc) return rc;
     cuuint64_t dims[2] = {(cuuint64_t)inner, (cuuint64_t)rows};
     cuuint64_t strides[1] = {(cuuint64_t)inner * 2};
-    cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+    cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
     cuuint32_t estr[2] = {1, 1};
+    static const int l2prom = [] { const char* e = getenv("B200PROBE_GEMM_L2_PROMOTION"); return e ? atoi(e) : 256; }();      // experiments: 0, 64, 128, 256
+    const CUtensorMapL2promotion prom = l2prom == 0 ? CU_TENSOR_MAP_L2_PROMOTION_NONE : l2prom == 64 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B
+                                      : l2prom == 128 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B : CU_TENSOR_MAP_L2_PROMOTION_L2_256B;
     CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                     box_cols == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B, prom, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { b200::set_error("cuTensorMapEncodeTiled failed: CUresult %d", (int)r); return B200PROBE_CUDA_BASE + 1; }
     return 0;
 }
@@ -616,16 +902,14 @@ uint16_t b200probe_gemm_operand_bits(uint64_t elem, uint32_t seed, int which) {
     return (which & 2) ? b200_gemm_uniform_bits(elem, seed, which & 1) : b200_gemm_elem_bits(elem, seed, which & 1);
 }
 
-// kernel variant: 2 = CTA-pair kernel (default when M is a multiple of 256), 1 = single-CTA kernel.
-// B200PROBE_GEMM_VARIANT overrides (tuning / A-B comparison).
+// kernel variant: 3 = CTA-pair kernel, 512 x 256 per pair (default when M is a multiple of 256; rows past M are zero-filled /
+// clipped by the tensor maps), 2 = CTA-pair kernel, 256 x 256 per pair with double-buffered accumulators, 1 = single-CTA kernel
+// (any M that is a multiple of 128).  B200PROBE_GEMM_VARIANT overrides, read per launch (tuning / A-B comparison).
 static int gemm_variant_for(int m) {
-    static int forced = -1;
-    if (forced < 0) {
-        const char* e = getenv("B200PROBE_GEMM_VARIANT");
-        forced = e ? atoi(e) : 0;
-    }
-    if (forced == 1) return 1;
-    return (m % (2 * BM) == 0) ? 2 : 1;
+    const char* e = getenv("B200PROBE_GEMM_VARIANT");
+    const int forced = e ? atoi(e) : 0;
+    if (forced == 1 || m % (2 * BM) != 0) return 1;
+    return forced == 2 ? 2 : 3;
 }
 
 int b200probe_gemm_launch(int ordinal, const void* a, const void* b, void* c, int m, int n, int k, void* stream) {
@@ -638,17 +922,35 @@ int b200probe_gemm_launch(int ordinal, const void* a, const void* b, void* c, in
     B200_CUDA_TRY(cudaSetDevice(ordinal));
     const int variant = gemm_variant_for(m);
     CUtensorMap ma, mb, mc;
-    rc = make_map(&ma, a, m, k, BM);
+    rc = make_map(&ma, a, m, k, variant == 3 ? 2 * BM : BM);
     if (rc) return rc;
-    rc = make_map(&mb, b, n, k, variant == 2 ? BN / 2 : BN);
+    rc = make_map(&mb, b, n, k, variant == 1 ? BN : BN / 2);
     if (rc) return rc;
-    rc = make_map(&mc, c, m, n, 32);            // the epilogue stores 32 rows x 64 columns per tensor store
+    rc = make_map(&mc, c, m, n, 32, variant == 3 ? 32 : EPI_UNIT_COLS);      // one tensor store = 32 rows x 64 (variant 3: 32) columns
     if (rc) return rc;
-    if (variant == 2) {
+    if (variant == 3) {
+        B200_CUDA_TRY(cudaFuncSetAttribute(gemm_bf16_tn_2cta_512_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM3_BYTES));
+        const int tiles = ((m + 4 * BM - 1) / (4 * BM)) * (n / BN);
+        const int pairs = std::min(tiles, props.sms / 2);
+        GemmTune tune{4, 0, 0, 0, 0, 0, 0};     // bands of 4 x 512 rows (the same 2048 rows as the 256 x 256 kernel's bands)
+        if (const char* e = getenv("B200PROBE_GEMM_PREFETCH")) { int v = atoi(e); if (v >= 0 && v <= 64) tune.prefetch = v; }
+        if (const char* e = getenv("B200PROBE_GEMM_EXPT")) tune.expt = atoi(e);
+        if (const char* e = getenv("B200PROBE_GEMM_EPI")) tune.epi = atoi(e);
+        if (const char* e = getenv("B200PROBE_GEMM_GROUP_M")) { int v = atoi(e); if (v >= 1 && v <= 64) tune.group_m = v; }
+        if (const char* e = getenv("B200PROBE_GEMM_POL_A")) tune.pol_a = atoi(e);
+        if (const char* e = getenv("B200PROBE_GEMM_POL_B")) tune.pol_b = atoi(e);
+        if (const char* e = getenv("B200PROBE_GEMM_POL_C")) tune.pol_c = atoi(e);
+        gemm_bf16_tn_2cta_512_kernel<<<2 * pairs, NUM_THREADS3, SMEM3_BYTES, (cudaStream_t)stream>>>(ma, mb, mc, (__nv_bfloat16*)c, m, n, k, tune);
+    } else if (variant == 2) {
         B200_CUDA_TRY(cudaFuncSetAttribute(gemm_bf16_tn_2cta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM2_BYTES));
         const int tiles = (m / (2 * BM)) * (n / BN);
         const int pairs = std::min(tiles, props.sms / 2);
-        gemm_bf16_tn_2cta_kernel<<<2 * pairs, NUM_THREADS, SMEM2_BYTES, (cudaStream_t)stream>>>(ma, mb, mc, m, n, k);
+        GemmTune tune{GROUP_M / 2, 0, 0, 0, 0, 0, 0};
+        if (const char* e = getenv("B200PROBE_GEMM_GROUP_M")) { int v = atoi(e); if (v >= 1 && v <= 64) tune.group_m = v; }
+        if (const char* e = getenv("B200PROBE_GEMM_POL_A")) tune.pol_a = atoi(e);
+        if (const char* e = getenv("B200PROBE_GEMM_POL_B")) tune.pol_b = atoi(e);
+        if (const char* e = getenv("B200PROBE_GEMM_POL_C")) tune.pol_c = atoi(e);
+        gemm_bf16_tn_2cta_kernel<<<2 * pairs, NUM_THREADS, SMEM2_BYTES, (cudaStream_t)stream>>>(ma, mb, mc, m, n, k, tune);
     } else {
         B200_CUDA_TRY(cudaFuncSetAttribute(gemm_bf16_tn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
         const int tiles = (m / BM) * (n / BN);

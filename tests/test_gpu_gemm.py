@@ -34,9 +34,17 @@ def bf16_bits(f32):
     return ((u + r) >> 16).astype(np.uint16)
 
 
-@pytest.mark.parametrize("m,n,k", [(128, 256, 64), (256, 512, 128), (384, 256, 320), (128, 768, 1024)])
-def test_whole_matrix_bit_exact_vs_oracle(env, m, n, k):
+# every kernel the launcher can pick: 512 x 256 per CTA pair with 32-byte stores from registers (default) or staged tensor stores,
+# 256 x 256 per CTA pair (double-buffered accumulators, tensor-store epilogue), single CTA
+KERNELS = {"pair512-stg": {}, "pair512-tma": {"B200PROBE_GEMM_EPI": "1"}, "pair256": {"B200PROBE_GEMM_VARIANT": "2"}, "single": {"B200PROBE_GEMM_VARIANT": "1"}}
+
+
+@pytest.mark.parametrize("kernel", sorted(KERNELS))
+@pytest.mark.parametrize("m,n,k", [(128, 256, 64), (256, 512, 128), (384, 256, 320), (128, 768, 1024), (512, 256, 192), (768, 512, 256), (1280, 256, 64)])
+def test_whole_matrix_bit_exact_vs_oracle(env, m, n, k, kernel, monkeypatch):
     torch, p, o = env
+    for kk, vv in KERNELS[kernel].items():
+        monkeypatch.setenv(kk, vv)          # read per launch by the library
     st = torch.cuda.current_stream().cuda_stream
     a = torch.empty(m * k, dtype=torch.int16, device="cuda:0")
     b = torch.empty(n * k, dtype=torch.int16, device="cuda:0")
