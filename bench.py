@@ -141,6 +141,8 @@ def nvml_poll_timing(o):
     try:
         if o.oracle_ph_open(None, None) != 0:
             return None
+        allowed = os.sched_getaffinity(0)
+        n_allowed = o.oracle_allowed_cpus()
         pinned_cpu = o.oracle_pin_self(0)                 # the single-thread figures are quoted pinned to one core
         o.oracle_ph_time_enumerate(10)
         o.oracle_ph_time_poll(10, 0)
@@ -148,7 +150,8 @@ def nvml_poll_timing(o):
         poll_us = o.oracle_ph_time_poll(1000, 0)
         out = {"enumerate_us": round(enum_us, 2), "poll_us": round(poll_us, 2), "polls_per_s": round(1e6 / max(poll_us, 1e-9)),
                "iters": 1000, "warmup": 10, "threads": 1, "pinned_to_cpu": pinned_cpu, "cpu_model": cpu_model(),
-               "host_cpus": os.cpu_count(), "allowed_cpus": o.oracle_allowed_cpus()}
+               "host_cpus": os.cpu_count(), "allowed_cpus": n_allowed}
+        os.sched_setaffinity(0, allowed)                  # the N-thread variant and everything after run unpinned again
         # N-thread variant: one thread per GPU, each with its own event set on its device
         pps = C.c_double()
         n_gpus = len(_oracle_verdicts(o))
@@ -630,6 +633,7 @@ def probe_round_leg(p):
     from k3s_nvidia_b200.labels import ActiveProbeRunner, PREFIX
 
     out = {}
+    os.environ["B200PROBE_IGNORE_TENANTS"] = "1"      # this bench has just loaded the GPU: to the runner it would look like a tenant
     try:
         with tempfile.TemporaryDirectory() as d:
             r = ActiveProbeRunner(p, features_dir=d, keep_arenas=True)
@@ -643,8 +647,11 @@ def probe_round_leg(p):
             out["gpus"] = p.device_count()
             out["labels"] = len(labels)
             out["gate"] = labels.get(f"{PREFIX}healthy")
+            out["what"] = "labels.ActiveProbeRunner.run_once(): busy query, HBM sweep 256 MiB-1 GiB x 3 modes, GEMM 8192^3, passive NVLink, exchange (>= 2 GPUs), labels written"
     except Exception as e:  # noqa: BLE001
         out["error"] = str(e)[:300]
+    finally:
+        os.environ.pop("B200PROBE_IGNORE_TENANTS", None)
     return out
 
 

@@ -322,9 +322,11 @@ public:
         for (int i = 0; i < n; ++i) b200probe_device_info(i, &infos[(size_t)i]);
         // who is on the devices?  asked once, before any probe of ours shows up in the utilisation figures
         std::map<int, std::string> state;
+        const char* ign = getenv("B200PROBE_IGNORE_TENANTS");            // benches / tests: the caller IS the tenant
+        const bool ignore_tenants = ign && *ign && strcmp(ign, "0") != 0;
         for (const auto& d : infos) {
             b200probe_busy_t busy;
-            state[d.index] = (b200probe_device_busy(d.index, &busy) == 0 && busy.busy) ? "busy" : "probed";
+            state[d.index] = (!ignore_tenants && b200probe_device_busy(d.index, &busy) == 0 && busy.busy) ? "busy" : "probed";
         }
         const bool explicit_hbm = getenv("B200PROBE_HBM_MIN_GBS") != nullptr, explicit_gemm = getenv("B200PROBE_GEMM_MIN_TFLOPS") != nullptr;
 

@@ -19,7 +19,8 @@ Tenants.  values.yaml:16-18 time-slices every GPU four ways, so a GPU carrying t
 The probes are gated against idle figures and would take SMs, HBM bandwidth and up to 4 GiB per device from
 the tenants, so a round first asks NVML who is on each device (b200probe_device_busy) and SKIPS busy devices:
 ``gpu<i>.probe-state=busy``, the last idle verdict of that GPU is carried over unchanged, and nothing of ours
-touches it.  A failed device allocation (B200PROBE_ENOMEM) is treated the same way (``no-memory``), never as
+touches it (B200PROBE_IGNORE_TENANTS=1 turns the check off: benches and tests, where the caller itself is the
+tenant).  A failed device allocation (B200PROBE_ENOMEM) is treated the same way (``no-memory``), never as
 unhealthy.  A GPU that has never been measured has no verdict and the gate label is absent (selectors on
 ``...healthy=true`` do not match: unknown is not healthy).  After every round all probe arenas are released.
 
@@ -375,9 +376,10 @@ class ActiveProbeRunner:
         infos = [self.probe.device_info(i) for i in range(n)]
         # who is on the devices?  asked once, before any probe of ours shows up in the utilisation figures
         state: Dict[int, str] = {}
+        ignore_tenants = os.environ.get("B200PROBE_IGNORE_TENANTS", "") not in ("", "0")      # benches / tests: the caller IS the tenant
         for d in infos:
             try:
-                state[d.index] = "busy" if self.probe.device_busy(d.index)["busy"] else "probed"
+                state[d.index] = "busy" if (not ignore_tenants and self.probe.device_busy(d.index)["busy"]) else "probed"
             except Exception as e:  # noqa: BLE001
                 log.warning("busy query failed on GPU %d (%s): probing it", d.index, e)
                 state[d.index] = "probed"

@@ -38,8 +38,12 @@ def test_native_list_and_watch_matches_nvml_enumeration(tmp_path):
         kubelet.stop()
 
 
-def test_native_probe_round_publishes_the_python_runner_label_set(tmp_path):
+def test_native_probe_round_publishes_the_python_runner_label_set(tmp_path, monkeypatch):
     import torch
+
+    # this pytest process holds a CUDA context and has just loaded the GPU: to the daemon it IS a tenant, and the round would
+    # (correctly) skip the device as busy.  The comparison needs both hosts to probe.
+    monkeypatch.setenv("B200PROBE_IGNORE_TENANTS", "1")
 
     from k3s_nvidia_b200 import labels as L
     from k3s_nvidia_b200.probe import Probe

@@ -143,10 +143,12 @@ def test_plugin_on_real_nvml(tmp_path):
         srv.stop(0)
 
 
-def test_active_probe_round_publishes_gate_label(tmp_path):
+def test_active_probe_round_publishes_gate_label(tmp_path, monkeypatch):
     """configs 3/5: probe results surfaced as NFD labels; the gate label is true on a healthy box."""
     from k3s_nvidia_b200 import labels as L
     from k3s_nvidia_b200.probe import Probe
+
+    monkeypatch.setenv("B200PROBE_IGNORE_TENANTS", "1")      # the test suite itself has just loaded this GPU
 
     p = Probe()
     try:
