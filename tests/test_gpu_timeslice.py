@@ -17,5 +17,6 @@ def test_four_probe_processes_share_one_gpu():
     for w in r["workers"]:
         assert (w["sum64"], w["xor32"]) == _oracle.pattern_checksum(o, nbytes // 4, 0xB200 + w["worker"])
         assert w["launches"] > 0
-    # time-slicing serialises the contexts: the aggregate stays near one process's bandwidth
-    assert r["aggregate_gbs"] > 3000, r
+    # time-slicing serialises the contexts: the aggregate stays near one process's bandwidth (5959 GB/s measured,
+    # profiles/timeslice_r01_4proc_1gpu.txt); the floor is 0.9 x that, so a regression of the kernel or of the sharing fails
+    assert r["aggregate_gbs"] > 0.9 * 5959, r

@@ -18,6 +18,7 @@ g = min(torch.cuda.device_count(), 8)
 S = int(os.environ.get("A2A_S", str(256 << 20)))
 REPS = 20
 ords = list(range(g))
+p.hbm_sweep(0, min_bytes=1 << 20, max_bytes=1 << 20, warmup=0, reps=1)       # first probe call: CUDA initialised, NVML index <-> CUDA ordinal resolved by UUID
 idx_of = {p.device_info(i).cuda_ordinal: i for i in range(p.device_count())}
 lines = [f"# NVLink counters, {g} GPUs, S = {S >> 20} MiB per pair, {REPS} timed exchanges + 2 warm-ups per row (PUSH_SYNC: + 3 drained matrix passes)",
          "# GB/s = per direction per GPU, payload bytes / median exchange time; NVML counters are per device, summed over its 18 links, KiB;",
