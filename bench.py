@@ -420,7 +420,10 @@ def run_ours(args):
                 "algorithmic_bytes_per_launch": nvlink["algorithmic_bytes_per_gpu_per_direction"], "traffic": None}
     if rank == 0:
         emit(line)
-    D.barrier()
+    # CPU-side wait: an NCCL barrier would park a spinning kernel on every waiting rank's GPU for as long as rank 0 works on its
+    # extras, and rank 0's probe round drives ALL GPUs from one process — its kernels would be time-sliced against those kernels
+    # (first seen as gpu0 "egress 234 GB/s": GPU 0 waiting 2 ms at the first step barrier for peers that had no time slice yet)
+    D.host_barrier()
     p.close()
     if world > 1:
         import torch.distributed as td
@@ -647,6 +650,8 @@ def probe_round_leg(p):
             out["gpus"] = p.device_count()
             out["labels"] = len(labels)
             out["gate"] = labels.get(f"{PREFIX}healthy")
+            out["nvlink_egress_labels"] = {k[len(PREFIX):]: v for k, v in sorted(labels.items()) if k.endswith("nvlink-egress-gbs")}
+            out["not_true"] = sorted(k[len(PREFIX):] + "=" + v for k, v in labels.items() if v == "false" or k.endswith("probe-state") and v != "probed")
             out["what"] = "labels.ActiveProbeRunner.run_once(): busy query, HBM sweep 256 MiB-1 GiB x 3 modes, GEMM 8192^3, passive NVLink, exchange (>= 2 GPUs), labels written"
     except Exception as e:  # noqa: BLE001
         out["error"] = str(e)[:300]

@@ -413,7 +413,7 @@ public:
             const int G = (int)ords.size();
             b200probe_a2a_cfg_t cfg;
             memset(&cfg, 0, sizeof(cfg));
-            cfg.warmup = 1; cfg.reps = 3; cfg.verify = 1;
+            cfg.warmup = 2; cfg.reps = 5; cfg.verify = 1;
             std::vector<double> pair((size_t)(G * G), 0.0);
             b200probe_a2a_result_t rep;
             const int rc = b200probe_nvlink_a2a(ords.data(), G, &cfg, pair.data(), &rep);

@@ -454,12 +454,13 @@ class ActiveProbeRunner:
             labels.update(nvlink_passive_labels(passive_before))
         except Exception as e:  # noqa: BLE001
             log.error("passive NVLink status failed: %s", e)
-        idle = [d for d in infos if state[d.index] == "probed" and d.cuda_ordinal >= 0]
+        # re-read the devices: CUDA ordinals are resolved (by UUID) by the first probe call of the process, not at enumeration
+        idle = [d for d in (self.probe.device_info(i) for i in range(n)) if state[d.index] == "probed" and d.cuda_ordinal >= 0]
         ran_nvlink = False
         if self.run_nvlink and len(idle) >= 2:
             ids = [d.index for d in idle]
             try:
-                rep = self.probe.nvlink_a2a([d.cuda_ordinal for d in idle], warmup=1, reps=3)
+                rep = self.probe.nvlink_a2a([d.cuda_ordinal for d in idle], warmup=2, reps=5)
                 labels.update(nvlink_labels(rep, self.th, ids))
                 labels.update(nvlink_localise(rep, ids, passive_before))
                 if labels.get(f"{PREFIX}nvlink-links-ok") == "false":
