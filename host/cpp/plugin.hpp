@@ -317,6 +317,10 @@ private:
                 logf("XidCriticalError: Xid=%llu on device %d; marking device as unhealthy", (unsigned long long)ev.event_data, ev.device_index);
                 mark_unhealthy_mask(ev.newly_unhealthy);
             }
+            // a wait that keeps failing (GPU_IS_LOST, UNINITIALIZED ...) returns at once: every device is already Unhealthy and
+            // there is nothing left to learn fast, so do not spin a core on it
+            if (ev.rc_wait != 0 /*NVML_SUCCESS*/ && ev.rc_wait != 10 /*NVML_ERROR_TIMEOUT*/)
+                for (int i = 0; i < 20 && !stopped(); ++i) std::this_thread::sleep_for(std::chrono::milliseconds(100));
         }
     }
 

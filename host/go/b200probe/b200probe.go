@@ -161,17 +161,48 @@ func NVLinkA2A(ordinals []int, bytesPerPair uint64, mode int) (pair []float64, e
 	for i := 0; i < g; i++ {
 		egress[i] = float64(res.egress_gbs[i])
 	}
+	// res.pair_source: 0 = shares of a concurrent exchange, 1 = isolated pairs, 2 = drained, device-stamped steps
 	return pair, egress, res.verified == 1, err
 }
 
 // GEMM runs the tcgen05 probe (0 = 8192 defaults) and returns median TFLOP/s and the data verdict.
-func GEMM(idx, m, n, k int) (tflops float64, verified bool, err error) {
+// operands: 0 = exact k/128 values (C bit-exact against fp64), 1 = Philox U(-1,1) (sampled outputs within tolerance).
+func GEMM(idx, m, n, k, operands int) (tflops float64, verified bool, err error) {
 	runtime.LockOSThread()
 	defer runtime.UnlockOSThread()
-	cfg := C.b200probe_gemm_cfg_t{m: C.int(m), n: C.int(n), k: C.int(k)}
+	cfg := C.b200probe_gemm_cfg_t{m: C.int(m), n: C.int(n), k: C.int(k), operands: C.int(operands)}
 	var res C.b200probe_gemm_result_t
 	err = check(C.b200probe_gemm(C.int(idx), &cfg, &res))
 	return float64(res.tflops_median), res.verified == 1, err
+}
+
+// ErrNoMem is B200PROBE_ENOMEM: a device allocation failed because tenants hold the memory. A resource verdict
+// ("inconclusive"), never a health verdict.
+const ErrNoMem = -10
+
+// Busy mirrors b200probe_busy_t: who else is on the device (asked before every probe round; busy devices are skipped).
+type Busy struct {
+	ComputeProcs, UtilGPUPct, UtilMemPct int
+	MemUsed                              uint64
+	Busy                                 bool
+}
+
+func DeviceBusy(idx int) (Busy, error) {
+	var b C.b200probe_busy_t
+	err := check(C.b200probe_device_busy(C.int(idx), &b))
+	return Busy{int(b.compute_procs), int(b.util_gpu_pct), int(b.util_mem_pct), uint64(b.mem_used), b.busy != 0}, err
+}
+
+// Release frees every resident probe arena of this process (HBM and GEMM buffers of the listed CUDA ordinals, the
+// exchange windows and communicators): called after every probe round so the daemon holds no device memory while tenants run.
+func Release(ordinals []int) {
+	runtime.LockOSThread()
+	defer runtime.UnlockOSThread()
+	for _, o := range ordinals {
+		C.b200probe_hbm_release(C.int(o))
+		C.b200probe_gemm_release(C.int(o))
+	}
+	C.b200probe_a2a_release()
 }
 
 // NVLinkStatus mirrors b200probe_nvlink_status_t: the passive NVML view of the links (state per link,

@@ -63,6 +63,8 @@ struct State {
     nvmlEventSet_t evset = nullptr;
     std::vector<uint64_t> skip_xids;
     uint64_t unhealthy = 0;
+    int waiters = 0;                      // threads inside nvmlEventSetWait_v2 with g.mu dropped
+    pthread_cond_t no_waiters = PTHREAD_COND_INITIALIZER;
     // cuda
     bool cuda_ready = false;
     int cuda_count = 0;
@@ -251,10 +253,18 @@ int health_wait_locked(int timeout_ms, b200probe_health_event_t* ev) {
     memset(&data, 0, sizeof(data));
     nvmlEventSet_t set = g.evset;
     auto wait = g.nvml.EventSetWait_v2;
-    // The wait blocks up to timeout_ms: drop the lock so enumeration / other devices' probes proceed.
+    // The wait blocks up to timeout_ms: drop the lock so enumeration / other devices' probes proceed.  health_close and
+    // shutdown wait for `waiters` to reach zero before they free the event set or unload NVML under a blocked waiter.
+    ++g.waiters;
     pthread_mutex_unlock(&g.mu);
     nvmlReturn_t r = wait(set, &data, timeout_ms < 0 ? 0 : (unsigned)timeout_ms);
     pthread_mutex_lock(&g.mu);
+    if (--g.waiters == 0) pthread_cond_broadcast(&g.no_waiters);
+    if (!g.health_open || g.evset != set) {          // closed (or closed and reopened) while we were waiting: the event belongs to nobody
+        ev->rc_wait = NVML_ERROR_TIMEOUT;
+        ev->skipped = 1;
+        return 0;
+    }
     ev->rc_wait = (int)r;
     if (r == NVML_ERROR_TIMEOUT) return 0;
     if (r != NVML_SUCCESS) {               // "Error waiting for event: marking all devices as unhealthy"
@@ -367,10 +377,17 @@ int b200probe_init(const char* path) {
     return 0;
 }
 
+// caller holds g.mu: a thread blocked in the event wait returns within its timeout; nothing it uses is freed before that
+static void drain_waiters_locked() {
+    g.health_open = false;                            // a waiter that wakes up sees the set is gone and reports a timeout
+    while (g.waiters > 0) pthread_cond_wait(&g.no_waiters, &g.mu);
+}
+
 void b200probe_shutdown(void) {
     Lock l;
     if (!g.inited) return;
-    if (g.health_open && g.evset) g.nvml.EventSetFree(g.evset);
+    drain_waiters_locked();
+    if (g.evset) g.nvml.EventSetFree(g.evset);
     g.evset = nullptr;
     g.health_open = g.health_disabled = false;
     g.unhealthy = 0;
@@ -482,6 +499,7 @@ int b200probe_health_mask(uint64_t* mask) {
 void b200probe_health_close(void) {
     Lock l;
     if (!g.inited || !g.health_open) return;
+    drain_waiters_locked();
     if (g.evset) g.nvml.EventSetFree(g.evset);
     g.evset = nullptr;
     g.health_open = g.health_disabled = false;

@@ -41,6 +41,15 @@ inline int cuda_rc(int cuda_err) { return cuda_err == 0 ? 0 : B200PROBE_CUDA_BAS
         }                                                                                     \
     } while (0)
 
+// A failed cudaMalloc is a RESOURCE verdict (a tenant holds the memory), not a CUDA fault: the host must be able to tell
+// the two apart (B200PROBE_ENOMEM -> "inconclusive", never "unhealthy").
+#define B200_ALLOC_TRY(expr)                                                                                  \
+    do {                                                                                                      \
+        cudaError_t e__ = (expr);                                                                             \
+        if (e__ == cudaErrorMemoryAllocation) { cudaGetLastError(); b200::set_error("%s: out of device memory", #expr); return B200PROBE_ENOMEM; } \
+        if (e__ != cudaSuccess) { b200::set_error("%s:%d %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(e__)); return b200::cuda_rc((int)e__); } \
+    } while (0)
+
 // ---- data pattern, shared host/device (header-only so the kernels inline it) -----------------
 #if defined(__CUDACC__)
 #define B200_HD __host__ __device__ __forceinline__

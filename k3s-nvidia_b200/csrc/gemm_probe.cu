@@ -842,12 +842,7 @@ void gemm_arena_free(GemmArena& g) {
     g.m = g.n = g.k = 0; g.operands = -1; g.samples_cap = 0; g.filled = false;
 }
 
-#define B200_ALLOC_TRY(expr)                                                                                  \
-    do {                                                                                                      \
-        cudaError_t e__ = (expr);                                                                             \
-        if (e__ == cudaErrorMemoryAllocation) { cudaGetLastError(); b200::set_error("%s: out of device memory", #expr); return B200PROBE_ENOMEM; } \
-        if (e__ != cudaSuccess) { b200::set_error("%s:%d %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(e__)); return b200::cuda_rc((int)e__); } \
-    } while (0)
+
 
 int gemm_arena_reserve(GemmArena& g, int M, int N, int K, int samples) {
     if (!g.stream) {

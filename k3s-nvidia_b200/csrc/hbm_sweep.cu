@@ -441,6 +441,7 @@ struct Arena {
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     uint64_t src_bytes = 0;                     // prefix of src currently holding pattern(src_seed)
     uint32_t src_seed = 0;
+    bool inited = false;                        // stream, events and partials all exist
 };
 Arena g_arena[B200PROBE_MAX_DEVICES];
 
@@ -466,30 +467,40 @@ void arena_free(Arena& a) {
     a.src = a.dst = a.flush = nullptr;
     a.partials = nullptr; a.e0 = a.e1 = nullptr; a.stream = nullptr;
     a.cap = a.flush_cap = a.src_bytes = 0;
+    a.inited = false;
 }
 
-int arena_reserve(Arena& a, uint64_t bytes, uint64_t flush_bytes) {
-    if (!a.stream) {
+int arena_reserve_inner(Arena& a, uint64_t bytes, uint64_t flush_bytes) {
+    if (!a.inited) {
         B200_CUDA_TRY(cudaStreamCreateWithFlags(&a.stream, cudaStreamNonBlocking));
         B200_CUDA_TRY(cudaEventCreate(&a.e0));
         B200_CUDA_TRY(cudaEventCreate(&a.e1));
-        B200_CUDA_TRY(cudaMalloc(&a.partials, 32));
+        B200_ALLOC_TRY(cudaMalloc(&a.partials, 32));
+        a.inited = true;                    // only now: a half-built arena is torn down by the caller, never reused
     }
     if (bytes > a.cap) {
         if (a.src) cudaFree(a.src);
         if (a.dst) cudaFree(a.dst);
         a.src = a.dst = nullptr; a.cap = 0; a.src_bytes = 0;
-        B200_CUDA_TRY(cudaMalloc(&a.src, bytes));
-        B200_CUDA_TRY(cudaMalloc(&a.dst, bytes));
+        B200_ALLOC_TRY(cudaMalloc(&a.src, bytes));
+        B200_ALLOC_TRY(cudaMalloc(&a.dst, bytes));
         a.cap = bytes;
     }
     if (flush_bytes > a.flush_cap) {
         if (a.flush) cudaFree(a.flush);
         a.flush = nullptr; a.flush_cap = 0;
-        B200_CUDA_TRY(cudaMalloc(&a.flush, flush_bytes));
+        B200_ALLOC_TRY(cudaMalloc(&a.flush, flush_bytes));
         a.flush_cap = flush_bytes;
     }
     return 0;
+}
+
+// Any failure (out of memory included) leaves NO arena behind: the next call starts from scratch instead of finding a stream
+// without its events, or a source buffer without its destination.
+int arena_reserve(Arena& a, uint64_t bytes, uint64_t flush_bytes) {
+    const int rc = arena_reserve_inner(a, bytes, flush_bytes);
+    if (rc) arena_free(a);
+    return rc;
 }
 
 // Verification launch: the TMA-ring read kernel with the pattern compare folded in (same staging and
@@ -661,7 +672,7 @@ int b200probe_hbm_release(int ordinal) {
     if (ordinal < 0 || ordinal >= B200PROBE_MAX_DEVICES) return B200PROBE_ERANGE;
     Arena& a = g_arena[ordinal];
     ArenaLock lock(a);
-    if (a.stream) { cudaSetDevice(ordinal); arena_free(a); }
+    if (a.stream || a.src) { cudaSetDevice(ordinal); arena_free(a); }
     return 0;
 }
 

@@ -490,13 +490,6 @@ struct A2aCtx {
 pthread_mutex_t g_ctx_mu = PTHREAD_MUTEX_INITIALIZER;     // also serialises the cross-device calls (header: "serialise internally")
 A2aCtx* g_ctx = nullptr;
 
-// a failed cudaMalloc is a RESOURCE verdict (a tenant holds the memory), not a CUDA fault: the host must be able to tell
-#define B200_ALLOC_TRY(expr)                                                                                  \
-    do {                                                                                                      \
-        cudaError_t e__ = (expr);                                                                             \
-        if (e__ == cudaErrorMemoryAllocation) { cudaGetLastError(); b200::set_error("%s: out of device memory", #expr); return B200PROBE_ENOMEM; } \
-        if (e__ != cudaSuccess) { b200::set_error("%s:%d %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(e__)); return b200::cuda_rc((int)e__); } \
-    } while (0)
 
 int ctx_build(A2aCtx* c, const int* ordinals, int g, uint64_t S, uint32_t seed) {
     c->g = g; c->S = S; c->seed = seed;

@@ -250,6 +250,8 @@ class DevicePlugin:
             if ev.newly_unhealthy:
                 log.info("XidCriticalError: Xid=%d on device %d; marking device as unhealthy", ev.event_data, ev.device_index)
                 self.mark_unhealthy_mask(ev.newly_unhealthy)
+            if ev.rc_wait not in (0, 10):       # neither SUCCESS nor TIMEOUT: a wait that keeps failing returns at once — back off, do not spin
+                self._stop.wait(2.0)
 
     def _kubelet_watch(self, period: float) -> None:
         """kubelet restart re-creates its socket: serve again and re-Register."""

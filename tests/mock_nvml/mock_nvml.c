@@ -13,6 +13,7 @@
  *   MOCK_NVML_LINKS_DOWN=d:l,d:l   link l of device d reports NVML_FEATURE_DISABLED
  *   MOCK_NVML_BUSY=d:procs:util,.. device d reports `procs` foreign compute processes (pids 40000+) and `util` % GPU
  *                                  utilisation (read at every query, so a test can change it between probe rounds)
+ *   MOCK_NVML_WAIT_FULL=1          an empty wait blocks for its whole timeout (default: at most 2 ms, to keep tests fast)
  *   MOCK_NVML_EVENT_FILE=path      events for a mock living in ANOTHER process (the native daemon): every
  *                                  wait first queues the lines "kind dev data" appended to the file since
  *                                  the last wait
@@ -188,7 +189,11 @@ nvmlReturn_t nvmlEventSetWait_v2(nvmlEventSet_t s, nvmlEventData_t* data, unsign
     drain_event_file();
     if (g_qh == g_qt) {
         pthread_mutex_unlock(&g_mu);
-        if (timeoutms) { struct timespec ts = {0, (long)(timeoutms > 2 ? 2 : timeoutms) * 1000000L}; nanosleep(&ts, NULL); }
+        if (timeoutms) {                 /* MOCK_NVML_WAIT_FULL=1: block for the whole timeout like the real driver (close-vs-wait tests) */
+            unsigned ms = getenv("MOCK_NVML_WAIT_FULL") ? timeoutms : (timeoutms > 2 ? 2 : timeoutms);
+            struct timespec ts = {ms / 1000, (long)(ms % 1000) * 1000000L};
+            nanosleep(&ts, NULL);
+        }
         return NVML_ERROR_TIMEOUT;
     }
     mev_t e = g_q[g_qh % 256];

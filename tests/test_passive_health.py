@@ -133,3 +133,40 @@ def test_wait_before_open_is_a_state_error(monkeypatch):
         assert e.value.rc == -11
     finally:
         p.close()
+
+
+def test_close_waits_for_a_thread_blocked_in_the_event_wait(monkeypatch):
+    """b200probe_health_wait drops the library lock around nvmlEventSetWait_v2; a concurrent health_close (or
+    shutdown) used to free the event set under the blocked waiter.  Close now waits until the waiter has left, and the waiter
+    that wakes up on a closed set reports a timeout instead of touching it."""
+    import threading
+    import time
+
+    from k3s_nvidia_b200.probe import Probe
+
+    monkeypatch.setenv("MOCK_NVML_DEVICES", "2")
+    monkeypatch.setenv("MOCK_NVML_WAIT_FULL", "1")
+    p = Probe(_oracle.MOCK_NVML)
+    try:
+        p.health_open("")
+        out = {}
+
+        def waiter():
+            t0 = time.perf_counter()
+            out["ev"] = p.health_wait(400)
+            out["dt"] = time.perf_counter() - t0
+
+        th = threading.Thread(target=waiter)
+        th.start()
+        time.sleep(0.08)
+        t0 = time.perf_counter()
+        p.health_close()                                    # must not return while the waiter is inside NVML
+        closed_after = time.perf_counter() - t0
+        th.join(5)
+        assert not th.is_alive()
+        assert closed_after > 0.25, f"close returned after {closed_after:.3f} s with a waiter still blocked"
+        assert out["dt"] > 0.35 and out["ev"].timed_out and out["ev"].newly_unhealthy == 0
+        assert p.health_open("") == 0                       # the library is in a clean state: open / wait work again
+        assert p.health_wait(1).timed_out
+    finally:
+        p.close()
