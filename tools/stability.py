@@ -24,10 +24,11 @@ def report(name, vals, unit):
 
 
 kw = dict(min_bytes=1 << 30, max_bytes=1 << 30, warmup=3, reps=20, verify=1)
-for mode, name in ((L.HBM_COPY, "copy"), (L.HBM_READ, "read"), (L.HBM_WRITE, "write")):
+ONLY_NVLINK = bool(os.environ.get("STAB_ONLY_NVLINK"))
+for mode, name in (() if ONLY_NVLINK else ((L.HBM_COPY, "copy"), (L.HBM_READ, "read"), (L.HBM_WRITE, "write"))):
     p.hbm_sweep(0, modes=mode, **kw)
     report(f"HBM {name} 1 GiB (median of 20 reps per call)", [p.hbm_sweep(0, modes=mode, **kw)[0].gbs_median for _ in range(N)], "GB/s")
-for cls, name in ((L.GEMM_EXACT, "k/128 operands"), (L.GEMM_UNIFORM, "U(-1,1) operands")):
+for cls, name in (() if ONLY_NVLINK else ((L.GEMM_EXACT, "k/128 operands"), (L.GEMM_UNIFORM, "U(-1,1) operands"))):
     p.gemm(0, warmup=3, reps=10, operands=cls)
     rs = [p.gemm(0, warmup=3, reps=10, operands=cls) for _ in range(N)]
     assert len({(r.c_sum64, r.c_xor32) for r in rs}) == 1, "C checksum changed run to run"
