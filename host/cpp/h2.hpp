@@ -75,6 +75,7 @@ struct Frame {
     uint8_t type = 0, flags = 0;
     uint32_t stream = 0;
     std::string payload;
+    bool oversize = false;
 };
 
 inline std::string frame_bytes(uint8_t type, uint8_t flags, uint32_t stream, const std::string& payload) {
@@ -87,12 +88,14 @@ inline std::string frame_bytes(uint8_t type, uint8_t flags, uint32_t stream, con
     f += payload;
     return f;
 }
+constexpr uint32_t kMaxFrameSize = 16384;          // RFC 9113 §4.2: the initial (and our only) SETTINGS_MAX_FRAME_SIZE
 inline bool read_frame(int fd, Frame* f, int deadline_ms = -1) {
     uint8_t h[9];
     if (!read_all(fd, h, 9, deadline_ms)) return false;
     const uint32_t n = ((uint32_t)h[0] << 16) | ((uint32_t)h[1] << 8) | h[2];
-    if (n > (1u << 24)) return false;
     f->type = h[3]; f->flags = h[4];
+    f->oversize = n > kMaxFrameSize;      // we never raise SETTINGS_MAX_FRAME_SIZE: a larger frame is a FRAME_SIZE_ERROR, and is not read
+    if (f->oversize) return false;
     f->stream = (((uint32_t)h[5] & 0x7f) << 24) | ((uint32_t)h[6] << 16) | ((uint32_t)h[7] << 8) | h[8];
     f->payload.resize(n);
     return n == 0 || read_all(fd, &f->payload[0], n, deadline_ms);
@@ -156,6 +159,7 @@ private:
     uint32_t id_;
     std::string path_, request_, header_block_;
     bool headers_done_ = false, request_done_ = false;
+    std::atomic<bool> dispatched_{false};        // handed to a worker thread: the reader must not touch request_ / header state any more
     bool headers_sent_ = false, finished_ = false;
     std::atomic<bool> cancelled_{false};
     int64_t send_window_ = 65535;
@@ -243,8 +247,12 @@ public:
                             call = std::make_shared<ServerCall>(this, f.stream, "");
                             call->send_window_ = peer_initial_window_;
                             calls_[f.stream] = call;
-                        } else call = it->second;                         // trailers from a client: not used by gRPC requests
+                        } else call = it->second;                         // a second header block on an open stream
                     }
+                    // gRPC clients send no trailers.  HEADERS on a stream whose request is complete (its worker may be reading
+                    // request_ and header state right now) is a protocol error; the block cannot simply be dropped either — it
+                    // would have to pass through the HPACK decoder — so the connection goes.
+                    if (call && (call->request_done_ || call->dispatched_.load())) { goaway(1); return; }
                     if (refused) {
                         // the block still has to pass through the HPACK decoder (it may update the dynamic table);
                         // simplest correct answer for a peer that ignores our SETTINGS is to drop the connection
@@ -276,6 +284,10 @@ public:
                         if (call && !(f.flags & END_STREAM)) write_frame(WINDOW_UPDATE, 0, f.stream, u32be((uint32_t)f.payload.size()));
                     }
                     if (!call) break;                                         // stream already reset/finished
+                    if (call->request_done_ || call->dispatched_.load()) {    // DATA after END_STREAM: the worker owns request_ now
+                        reset(f.stream, 5);                                   // STREAM_CLOSED
+                        break;
+                    }
                     call->request_.append(f.payload, off, f.payload.size() - off - pad);
                     if (call->request_.size() > (4u << 20)) { reset(f.stream, 11); drop(f.stream); break; }
                     if (f.flags & END_STREAM) { call->request_done_ = true; dispatch(call); }
@@ -297,6 +309,7 @@ public:
                     break;                                                    // unknown frame types are ignored (RFC 9113 §4.1)
             }
         }
+        if (f.oversize) goaway(6);                                            // FRAME_SIZE_ERROR
         cancel_all();
     }
 
@@ -378,6 +391,7 @@ private:
         return true;
     }
     void dispatch(const std::shared_ptr<ServerCall>& call) {
+        if (call->dispatched_.exchange(true)) return;                      // one worker per call, whatever the peer sends afterwards
         auto it = routes_->find(call->path_);
         if (it == routes_->end()) { call->finish({UNIMPLEMENTED, "unknown method " + call->path_}); return; }
         std::vector<std::string> msgs;

@@ -834,6 +834,67 @@ def test_random_frame_sequences_never_crash_the_transport(stack):
         assert dict(r.container_responses[0].envs) == {"NVIDIA_VISIBLE_DEVICES": U0}
 
 
+def test_frames_on_a_finished_stream_and_oversize_frames_are_refused(stack):
+    """DATA after END_STREAM used to append to the request a worker was already reading and dispatch the call a
+    second time; frames above SETTINGS_MAX_FRAME_SIZE (never raised: 16384) were read up to 16 MiB.  Now: RST_STREAM
+    (STREAM_CLOSED) for the late DATA and exactly one response; GOAWAY(FRAME_SIZE_ERROR) without reading the oversize frame."""
+    import socket
+    import struct
+
+    kubelet, daemon = stack
+    path = os.path.join(daemon.dir, "nvidia-gpu.sock")
+
+    def frame(t, flags, stream, payload=b""):
+        return struct.pack(">I", len(payload))[1:] + bytes([t, flags]) + struct.pack(">I", stream & 0x7FFFFFFF) + payload
+
+    def read_frames(sock, seconds=1.0):
+        sock.settimeout(0.2)
+        buf, t_end = b"", time.time() + seconds
+        while time.time() < t_end:
+            try:
+                chunk = sock.recv(65536)
+            except socket.timeout:
+                continue
+            except ConnectionError:
+                break
+            if not chunk:
+                break
+            buf += chunk
+        out = []
+        while len(buf) >= 9:
+            n = int.from_bytes(buf[:3], "big")
+            out.append((buf[3], buf[4], int.from_bytes(buf[5:9], "big") & 0x7FFFFFFF, buf[9:9 + n]))
+            buf = buf[9 + n:]
+        return out
+
+    hdr = b"\x83\x86\x44\x1e/v1beta1.DevicePlugin/Allocate" + b"\x41\x09localhost" + b"\x5f\x10application/grpc" + b"\x40\x02te\x08trailers"
+    req = api.AllocateRequest(container_requests=[api.ContainerAllocateRequest(devices_ids=[f"{U0}::0"])]).SerializeToString()
+    body = b"\x00" + struct.pack(">I", len(req)) + req
+    s = socket.socket(socket.AF_UNIX, socket.SOCK_STREAM)
+    s.connect(path)
+    s.sendall(b"PRI * HTTP/2.0\r\n\r\nSM\r\n\r\n" + frame(4, 0, 0) + frame(1, 4, 1, hdr) + frame(0, 1, 1, body)      # a complete unary call ...
+              + frame(0, 1, 1, body))                                                                                     # ... and DATA + END_STREAM again
+    got = read_frames(s)
+    s.close()
+    rst = [f for f in got if f[0] == 3 and f[2] == 1]
+    assert rst and int.from_bytes(rst[0][3], "big") == 5, got                      # RST_STREAM(STREAM_CLOSED) for the late DATA
+    data = [f for f in got if f[0] == 0 and f[2] == 1]
+    assert len(data) == 1, "the call must be answered exactly once"
+    resp = api.AllocateResponse.FromString(data[0][3][5:])
+    assert dict(resp.container_responses[0].envs) == {"NVIDIA_VISIBLE_DEVICES": U0}
+    # oversize frame: only the 9-byte header is sent; a reader that waited for the body would hang instead of answering
+    s = socket.socket(socket.AF_UNIX, socket.SOCK_STREAM)
+    s.connect(path)
+    s.sendall(b"PRI * HTTP/2.0\r\n\r\nSM\r\n\r\n" + frame(4, 0, 0) + struct.pack(">I", 16385)[1:] + bytes([0, 0]) + struct.pack(">I", 1))
+    got = read_frames(s)
+    s.close()
+    goaway = [f for f in got if f[0] == 7]
+    assert goaway and int.from_bytes(goaway[0][3][4:8], "big") == 6, got             # FRAME_SIZE_ERROR
+    assert daemon.proc.poll() is None
+    with kubelet.plugin_channel() as ch:
+        assert len(next(api.DevicePluginStub(ch).ListAndWatch(api.Empty())).devices) == 8
+
+
 def test_committed_huffman_table_is_what_libnghttp2_implements(tmp_path):
     """host/cpp/hpack_huffman.inc regenerated from the system libnghttp2 (tools/gen_hpack_huffman.py) is byte-identical
     to the committed file: the table is pinned to an independent implementation of RFC 7541 Appendix B."""

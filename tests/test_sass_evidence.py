@@ -42,6 +42,13 @@ def test_gemm_probe_is_tcgen05_with_tma_and_tmem(sass):
         assert "HMMA." not in s.replace("UTCHMMA", "") and "HGMMA" not in s  # no legacy mma.sync / Hopper wgmma path
     assert "UTCHMMA.2CTA" in _of(sass, "gemm_bf16_tn_2cta_kernel")           # cta_group::2
     assert "UTCBAR.2CTA.MULTICAST" in _of(sass, "gemm_bf16_tn_2cta_kernel")  # commit multicast to both CTAs' barriers
+    # the 256 x 256 kernels leave through tensor stores; the shipped 512 x 256 kernel has both epilogues compiled in:
+    # 32-byte stores straight from registers (default) and the staged tensor store
+    assert "UTMASTG" in _of(sass, "gemm_bf16_tn_2cta_kernel") and "UTMASTG" in _of(sass, "gemm_bf16_tn_kernel")
+    big = _of(sass, "gemm_bf16_tn_2cta_512_kernel")
+    assert "UTCHMMA.2CTA" in big and "UTMALDG" in big and "UTCBAR.2CTA.MULTICAST" in big and "HMMA." not in big.replace("UTCHMMA", "")
+    assert "STG.E.ENL2.256" in big and "UTMASTG" in big
+    assert big.count("LDTM.x32") >= 16                                       # two register sets of tcgen05.ld in flight, both epilogues
 
 
 def test_hbm_ring_kernels_move_data_with_bulk_tma(sass):
