@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libb200probe.so")
+LIB_PATH = os.environ.get("B200PROBE_LIB") or os.path.join(_HERE, "libb200probe.so")     # B200PROBE_LIB: another build of the SAME library (kernel experiments); there is still no fallback
 
 ABI_VERSION = 2
 MAX_DEVICES = 64

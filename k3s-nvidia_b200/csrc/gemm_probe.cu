@@ -324,6 +324,7 @@ struct GemmTune {
     int prefetch;           // 512 x 256 kernel: k-blocks by which an L2 prefetch of the operand boxes runs ahead of the loads (0 = none)
     int expt;               // attribution experiments (WRONG results): 1 = the epilogue hands the accumulators back without reading them
     int epi;                // 512 x 256 kernel epilogue: 0 = 32-byte stores from registers (default), 1 = staged tensor stores
+    int skew;               // 512 x 256 kernel: k-blocks by which accumulator 1 runs behind accumulator 0 (0..3), see the MMA issuer
 };
 __device__ __forceinline__ void tma_prefetch_l2_2d(const CUtensorMap* map, int c0, int c1) {
     asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"((uint64_t)map), "r"(c0), "r"(c1) : "memory");
@@ -593,9 +594,9 @@ gemm_bf16_tn_2cta_512_kernel(const __grid_constant__ CUtensorMap tma_a, const __
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem_epi + EPI_BYTES);
     uint64_t* full = bars;                   // [STAGES3]  used in the leader only
     uint64_t* empty = bars + STAGES3;        // [STAGES3]  one per CTA, signalled by multicast commit
-    uint64_t* tfull = bars + 2 * STAGES3;    // one per CTA, signalled by multicast commit: both accumulators of the tile are complete
-    uint64_t* tempty = tfull + 1;            // leader only: the 8 epilogue warps of the pair have both accumulators in registers
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 1);
+    uint64_t* tfull = bars + 2 * STAGES3;    // [2] one per accumulator and CTA, signalled by multicast commit: accumulator h of the tile is complete
+    uint64_t* tempty = tfull + 2;            // [2] leader only: the 4 + 4 epilogue warps of accumulator h have it in registers
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t cta_rank = cluster_ctarank();
@@ -611,8 +612,7 @@ gemm_bf16_tn_2cta_512_kernel(const __grid_constant__ CUtensorMap tma_a, const __
     }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < STAGES3; ++s) { mbar_init(smem_u32(&full[s]), 1); mbar_init(smem_u32(&empty[s]), 1); }
-        mbar_init(smem_u32(tfull), 1);
-        mbar_init(smem_u32(tempty), 16);                                   // 8 epilogue warps in each CTA of the pair
+        for (int h = 0; h < 2; ++h) { mbar_init(smem_u32(&tfull[h]), 1); mbar_init(smem_u32(&tempty[h]), 8); }    // 4 warps per accumulator in each CTA
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {
@@ -658,40 +658,64 @@ gemm_bf16_tn_2cta_512_kernel(const __grid_constant__ CUtensorMap tma_a, const __
         }
     } else if (warp == 1) {
         if (leader && lane == 0) {                         // ===== MMA issuer (leader CTA only) =====
-            uint32_t stage = 0, phase = 0, it = 0;
-            for (int t = pair; t < num_tiles; t += num_pairs, ++it) {
-                mbar_wait(smem_u32(tempty), (it & 1) ^ 1);                 // the epilogue has drained the previous tile's accumulators
-                tc_fence_after();
-                for (int kb = 0; kb < num_kb; ++kb) {
-                    mbar_wait(smem_u32(&full[stage]), phase);
-                    tc_fence_after();
-                    const uint64_t a_desc = make_smem_desc(smem_u32(smem_a + stage * A3_STAGE_BYTES));
-                    const uint64_t b_desc = make_smem_desc(smem_u32(smem_b + stage * B3_STAGE_BYTES));
+            // Accumulator 1 runs `d` k-blocks behind accumulator 0.  Both accumulators fill TMEM, so a tile's epilogue cannot hide
+            // behind the next tile's MMAs as a whole — but with the skew accumulator 0 completes d blocks early and is drained
+            // (TMEM reads: 64 B/clk, 2048 clocks per accumulator) while the tensor pipe still works on accumulator 1's last d
+            // blocks, and accumulator 1 is drained under the next tile's first d blocks of accumulator 0.  A stage is released
+            // when accumulator 1 has consumed it, so the loads' lookahead shrinks from STAGES3 to STAGES3 - d blocks.
+            //   per tile:  A  acc0 blocks [0, d)                 B  acc1 block kb-d, acc0 block kb  (kb in [d, num_kb))
+            //              C  acc1 blocks [num_kb-d, num_kb)     tfull[0] after B, tfull[1] after C;  d = 0: the plain order
+            // MEASURED (tools/gemm_tune.py, 8192^3, sustained): d = 0 1432, d = 1 1422, d = 2 1312, d = 3 943 TFLOP/s — with four 48 KiB
+            // stages the lost lookahead costs more than the hidden drain gains, so the default is d = 0 (B200PROBE_GEMM_SKEW).
+            const int d = max(0, min(tune.skew, min(num_kb - 1, STAGES3 - 1)));
+            long long g0 = 0, g1 = 0;                          // k-blocks consumed so far by accumulator 0 / 1 (the stage ring index)
+            auto issue = [&](long long g, int h, int kb) {
+                const uint32_t stage = (uint32_t)(g % STAGES3);
+                const uint64_t a_desc = make_smem_desc(smem_u32(smem_a + stage * A3_STAGE_BYTES)) + (uint64_t)(h * ((BM * BK * 2) >> 4));
+                const uint64_t b_desc = make_smem_desc(smem_u32(smem_b + stage * B3_STAGE_BYTES));
 #pragma unroll
-                    for (int k = 0; k < BK / UMMA_K; ++k) {
-                        umma_bf16_2sm(tmem_base, a_desc + (uint64_t)(k * 2), b_desc + (uint64_t)(k * 2), kIdesc2, (kb | k) != 0);
-                        umma_bf16_2sm(tmem_base + BN, a_desc + (uint64_t)((BM * BK * 2) >> 4) + (uint64_t)(k * 2), b_desc + (uint64_t)(k * 2), kIdesc2, (kb | k) != 0);
-                    }
-                    umma_commit_2sm(smem_u32(&empty[stage]));
-                    if (++stage == STAGES3) { stage = 0; phase ^= 1; }
+                for (int k = 0; k < BK / UMMA_K; ++k)
+                    umma_bf16_2sm(tmem_base + h * BN, a_desc + (uint64_t)(k * 2), b_desc + (uint64_t)(k * 2), kIdesc2, (kb | k) != 0);
+            };
+            auto wait_full = [&](long long g) {
+                mbar_wait(smem_u32(&full[g % STAGES3]), (uint32_t)((g / STAGES3) & 1));
+                tc_fence_after();
+            };
+            uint32_t it = 0;
+            for (int t = pair; t < num_tiles; t += num_pairs, ++it) {
+                mbar_wait(smem_u32(&tempty[0]), (it & 1) ^ 1);             // accumulator 0 of the previous tile is in registers
+                tc_fence_after();
+                for (int kb = 0; kb < d; ++kb, ++g0) { wait_full(g0); issue(g0, 0, kb); }
+                mbar_wait(smem_u32(&tempty[1]), (it & 1) ^ 1);
+                tc_fence_after();
+                for (int kb = d; kb < num_kb; ++kb, ++g0, ++g1) {
+                    wait_full(g0);
+                    issue(g1, 1, kb - d);
+                    umma_commit_2sm(smem_u32(&empty[g1 % STAGES3]));       // both accumulators are done with that stage
+                    issue(g0, 0, kb);
                 }
-                umma_commit_2sm(smem_u32(tfull));
+                umma_commit_2sm(smem_u32(&tfull[0]));
+                for (int kb = num_kb - d; kb < num_kb; ++kb, ++g1) {
+                    issue(g1, 1, kb);
+                    umma_commit_2sm(smem_u32(&empty[g1 % STAGES3]));
+                }
+                umma_commit_2sm(smem_u32(&tfull[1]));
             }
         }
     } else if (warp >= 4) {                                // ===== epilogue (both CTAs): warp -> accumulator h, TMEM lane quadrant q =====
         const int q = warp & 3, h = (warp - 4) >> 2;       // a warp may read TMEM lanes [32 (warp % 4), +32)
         uint32_t it = 0, ubuf = 0;
         const uint64_t polc = l2_policy(tune.pol_c);
-        const uint32_t tempty_bar = smem_u32(tempty);
+        const uint32_t tempty_bar = smem_u32(&tempty[h]);
         uint8_t* const stage = smem_epi + (warp - 4) * 2 * EPI32_BUF_BYTES;
         for (int t = pair; t < num_tiles; t += num_pairs, ++it) {
             const TileCoord tc = tile_coord3(t, num_m, num_n, tune.group_m);
-            mbar_wait(smem_u32(tfull), it & 1);
+            mbar_wait(smem_u32(&tfull[h]), it & 1);
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + h * BN;
             const int row0 = tc.m0 + (int)cta_rank * 2 * BM + h * BM + q * 32;
             auto release = [&]() {
-                tc_fence_before();                         // this warp's slice is in registers: 16 such arrivals free both accumulators
+                tc_fence_before();                         // this warp's slice is in registers: 8 such arrivals free accumulator h
                 __syncwarp();
                 if (lane == 0) mbar_arrive_leader(tempty_bar);
             };
@@ -702,7 +726,7 @@ gemm_bf16_tn_2cta_512_kernel(const __grid_constant__ CUtensorMap tma_a, const __
                 continue;
             }
             epilogue_slice32(taddr, stage, ubuf, &tma_c, row0, tc.n0, lane, [&]() {
-                tc_fence_before();                         // this warp's slice is in registers: 16 such arrivals free both accumulators
+                tc_fence_before();                         // this warp's slice is in registers: 8 such arrivals free accumulator h
                 __syncwarp();
                 if (lane == 0) mbar_arrive_leader(tempty_bar);
             }, polc);
@@ -927,10 +951,11 @@ int b200probe_gemm_launch(int ordinal, const void* a, const void* b, void* c, in
         B200_CUDA_TRY(cudaFuncSetAttribute(gemm_bf16_tn_2cta_512_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM3_BYTES));
         const int tiles = ((m + 4 * BM - 1) / (4 * BM)) * (n / BN);
         const int pairs = std::min(tiles, props.sms / 2);
-        GemmTune tune{4, 0, 0, 0, 0, 0, 0};     // bands of 4 x 512 rows (the same 2048 rows as the 256 x 256 kernel's bands)
+        GemmTune tune{4, 0, 0, 0, 0, 0, 0, 0};  // bands of 4 x 512 rows (the same 2048 rows as the 256 x 256 kernel's bands)
         if (const char* e = getenv("B200PROBE_GEMM_PREFETCH")) { int v = atoi(e); if (v >= 0 && v <= 64) tune.prefetch = v; }
         if (const char* e = getenv("B200PROBE_GEMM_EXPT")) tune.expt = atoi(e);
         if (const char* e = getenv("B200PROBE_GEMM_EPI")) tune.epi = atoi(e);
+        if (const char* e = getenv("B200PROBE_GEMM_SKEW")) tune.skew = atoi(e);
         if (const char* e = getenv("B200PROBE_GEMM_GROUP_M")) { int v = atoi(e); if (v >= 1 && v <= 64) tune.group_m = v; }
         if (const char* e = getenv("B200PROBE_GEMM_POL_A")) tune.pol_a = atoi(e);
         if (const char* e = getenv("B200PROBE_GEMM_POL_B")) tune.pol_b = atoi(e);
@@ -940,7 +965,7 @@ int b200probe_gemm_launch(int ordinal, const void* a, const void* b, void* c, in
         B200_CUDA_TRY(cudaFuncSetAttribute(gemm_bf16_tn_2cta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM2_BYTES));
         const int tiles = (m / (2 * BM)) * (n / BN);
         const int pairs = std::min(tiles, props.sms / 2);
-        GemmTune tune{GROUP_M / 2, 0, 0, 0, 0, 0, 0};
+        GemmTune tune{GROUP_M / 2, 0, 0, 0, 0, 0, 0, 0};
         if (const char* e = getenv("B200PROBE_GEMM_GROUP_M")) { int v = atoi(e); if (v >= 1 && v <= 64) tune.group_m = v; }
         if (const char* e = getenv("B200PROBE_GEMM_POL_A")) tune.pol_a = atoi(e);
         if (const char* e = getenv("B200PROBE_GEMM_POL_B")) tune.pol_b = atoi(e);

@@ -1,7 +1,7 @@
 #!/bin/bash
+# GEMM skew experiment on the experimental build of the library
 mkdir -p gpurun_out
 export CUDA_VISIBLE_DEVICES=0
-M=gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,dram__cycles_elapsed.avg,dram__cycles_active.avg,dram__cycles_active_read.avg,dram__cycles_active_write.avg,dram__throughput.avg.pct_of_peak_sustained_elapsed,lts__throughput.avg.pct_of_peak_sustained_elapsed,lts__t_sector_hit_rate.pct
-timeout 600 ncu --metrics $M --clock-control none -k regex:hbm_ring_kernel -c 40 --csv --log-file gpurun_out/ncu_hbm_dram_counters.csv python tools/prof_hbm.py > gpurun_out/prof_hbm.log 2>&1; tail -1 gpurun_out/prof_hbm.log
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:hbm_ring_kernel -s 12 -c 2 -f -o gpurun_out/prof_hbm_copy_r02 python bench.py --steps 20 --warmup 3 --no-cpu-baseline --no-gemm --no-probe-round > gpurun_out/bench_under_ncu2.log 2>&1
-ls -la gpurun_out/*.ncu-rep
+export B200PROBE_LIB=$PWD/k3s-nvidia_b200/libb200probe_exp.so
+for sk in 0 2 1 3; do echo "== skew $sk"; B200PROBE_GEMM_SKEW=$sk timeout 600 python -m pytest tests/test_gpu_gemm.py -m gpu -x -q -k "pair512 or headline" 2>&1 | tail -3; done
+GEMM_TUNE_QUICK=1 timeout 900 python tools/gemm_tune.py 2>&1 | tail -26
