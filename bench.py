@@ -286,6 +286,7 @@ def run_ours(args):
         sus_ms += a_.elapsed_time(b_)
         sus_n += 256
     sampler.stop()
+    clocks = sampler.summary()             # taken NOW: the timed K steps + the >= 1 s sustained window, nothing else
     sustained = D.aggregate_bandwidth(2.0 * nbytes * sus_n, sus_ms)
     agg = D.aggregate_bandwidth(2.0 * nbytes * args.steps, ms_local)
     launch_ms = ms_local / args.steps
@@ -356,7 +357,7 @@ def run_ours(args):
         p.lib.b200probe_hbm_release(local_rank)
 
         peaks, peak_src = measured_peaks()
-        gemm = None if args.no_gemm else gemm_leg(torch, p, local_rank, nvml_index, peaks, sampler)
+        gemm = None if args.no_gemm else gemm_leg(torch, p, local_rank, nvml_index, peaks, ClockSampler(nvml_index))
         probe_round = None if args.no_probe_round else probe_round_leg(p)
         traffic = None
         try:
@@ -396,7 +397,7 @@ def run_ours(args):
                             "roundtrip_identical": hostbuf_ok,
                             "what": "b200probe_hbm_copy_host: pinned host src -> H2D -> copy kernel + checksum -> D2H host dst, 8 MiB chunks pipelined on 3 streams (PCIe-bound: 2N bytes counted, N each way)"},
             "gpu_launches": args.steps * world,
-            "clocks": sampler.summary(),
+            "clocks": clocks,
             "hbm_read_gbs": round(rd, 1), "hbm_write_gbs": round(wr, 1),
             "hbm_sustained": {"value": round(sustained["gbs"], 2), "unit": "GB/s", "seconds": round(sustained["ms"] / 1e3, 3), "launches_per_rank": sus_n,
                               "what": "the same copy launch back to back for >= 1 s after the timed K steps (aggregate over ranks, max-over-ranks time)"},
@@ -599,8 +600,9 @@ def gemm_leg(torch, p, ordinal, nvml_index, peaks, sampler):
         lmed, lbest = burst(cublas)
         sampler.start()
         sus = sustained(ours)
-        clk = sampler.summary()
         sampler.stop()
+        clk = sampler.summary()
+        sampler.reasons.clear()
         lsus = sustained(cublas)
         ours()
         cublas()
