@@ -325,8 +325,6 @@ struct GemmTune {
     int expt;               // attribution experiments (WRONG results): 1 = the epilogue hands the accumulators back without reading them
     int epi;                // 512 x 256 kernel epilogue: 0 = 32-byte stores from registers (default), 1 = staged tensor stores
     int skew;               // 512 x 256 kernel: k-blocks by which accumulator 1 runs behind accumulator 0 (0..3), see the MMA issuer
-    int smid_map;           // 512 x 256 kernel: 1 = a pair's tile sequence is chosen by the leader's SM id (>> 1) instead of its cluster
-                            // index, so pairs that sit next to each other on the chip work on neighbouring tiles (shared operand rows)
 };
 __device__ __forceinline__ void tma_prefetch_l2_2d(const CUtensorMap* map, int c0, int c1) {
     asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"((uint64_t)map), "r"(c0), "r"(c1) : "memory");
@@ -605,9 +603,8 @@ gemm_bf16_tn_2cta_512_kernel(const __grid_constant__ CUtensorMap tma_a, const __
     const bool leader = cta_rank == 0;
     // rows past M are zero-filled by the tensor loads and clipped by the tensor stores: any M that is a multiple of 128 works
     const int num_m = (M + 4 * BM - 1) / (4 * BM), num_n = N / BN, num_tiles = num_m * num_n, num_kb = K / BK;
-    int pair = blockIdx.x >> 1;
-    const int num_pairs = gridDim.x >> 1;
-    uint32_t* const pair_slot = tmem_slot + 1;             // smid_map: the leader publishes the pair's index here
+    // cluster i sits on SMs 2(i-3), 2(i-3)+1 (tools/smid_probe.cu): consecutive pairs are neighbours on the chip already
+    const int pair = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
 
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tma_a) : "memory");
@@ -615,7 +612,6 @@ gemm_bf16_tn_2cta_512_kernel(const __grid_constant__ CUtensorMap tma_a, const __
         asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tma_c) : "memory");
     }
     if (warp == 1 && lane == 0) {
-        if (leader) { uint32_t smid; asm volatile("mov.u32 %0, %%smid;" : "=r"(smid)); *pair_slot = smid >> 1; }
         for (int s = 0; s < STAGES3; ++s) { mbar_init(smem_u32(&full[s]), 1); mbar_init(smem_u32(&empty[s]), 1); }
         for (int h = 0; h < 2; ++h) { mbar_init(smem_u32(&tfull[h]), 1); mbar_init(smem_u32(&tempty[h]), 8); }    // 4 warps per accumulator in each CTA
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -628,12 +624,6 @@ gemm_bf16_tn_2cta_512_kernel(const __grid_constant__ CUtensorMap tma_a, const __
     cluster_sync_all();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    if (tune.smid_map && num_pairs == 74) {                // both CTAs take the LEADER's value (read over the cluster's shared memory)
-        uint32_t remote, v;
-        asm volatile("mapa.shared::cluster.u32 %0, %1, 0;" : "=r"(remote) : "r"(smem_u32(pair_slot)));
-        asm volatile("ld.shared::cluster.u32 %0, [%1];" : "=r"(v) : "r"(remote) : "memory");
-        pair = (int)v;
-    }
 
     if (warp == 0) {
         if (lane == 0) {                                   // ===== TMA producer (both CTAs) =====
@@ -962,12 +952,11 @@ int b200probe_gemm_launch(int ordinal, const void* a, const void* b, void* c, in
         B200_CUDA_TRY(cudaFuncSetAttribute(gemm_bf16_tn_2cta_512_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM3_BYTES));
         const int tiles = ((m + 4 * BM - 1) / (4 * BM)) * (n / BN);
         const int pairs = std::min(tiles, props.sms / 2);
-        GemmTune tune{4, 0, 0, 0, 0, 0, 0, 0, 0};   // bands of 4 x 512 rows (the same 2048 rows as the 256 x 256 kernel's bands)
+        GemmTune tune{4, 0, 0, 0, 0, 0, 0, 0};  // bands of 4 x 512 rows (the same 2048 rows as the 256 x 256 kernel's bands)
         if (const char* e = getenv("B200PROBE_GEMM_PREFETCH")) { int v = atoi(e); if (v >= 0 && v <= 64) tune.prefetch = v; }
         if (const char* e = getenv("B200PROBE_GEMM_EXPT")) tune.expt = atoi(e);
         if (const char* e = getenv("B200PROBE_GEMM_EPI")) tune.epi = atoi(e);
         if (const char* e = getenv("B200PROBE_GEMM_SKEW")) tune.skew = atoi(e);
-        if (const char* e = getenv("B200PROBE_GEMM_SMID_MAP")) tune.smid_map = atoi(e);
         if (const char* e = getenv("B200PROBE_GEMM_GROUP_M")) { int v = atoi(e); if (v >= 1 && v <= 64) tune.group_m = v; }
         if (const char* e = getenv("B200PROBE_GEMM_POL_A")) tune.pol_a = atoi(e);
         if (const char* e = getenv("B200PROBE_GEMM_POL_B")) tune.pol_b = atoi(e);
@@ -977,7 +966,7 @@ int b200probe_gemm_launch(int ordinal, const void* a, const void* b, void* c, in
         B200_CUDA_TRY(cudaFuncSetAttribute(gemm_bf16_tn_2cta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM2_BYTES));
         const int tiles = (m / (2 * BM)) * (n / BN);
         const int pairs = std::min(tiles, props.sms / 2);
-        GemmTune tune{GROUP_M / 2, 0, 0, 0, 0, 0, 0, 0, 0};
+        GemmTune tune{GROUP_M / 2, 0, 0, 0, 0, 0, 0, 0};
         if (const char* e = getenv("B200PROBE_GEMM_GROUP_M")) { int v = atoi(e); if (v >= 1 && v <= 64) tune.group_m = v; }
         if (const char* e = getenv("B200PROBE_GEMM_POL_A")) tune.pol_a = atoi(e);
         if (const char* e = getenv("B200PROBE_GEMM_POL_B")) tune.pol_b = atoi(e);

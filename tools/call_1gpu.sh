@@ -1,8 +1,7 @@
 #!/bin/bash
-# round 2, 1-GPU: what the driver runs at round end (tests, smoke, bench both arms)
 mkdir -p gpurun_out
 export CUDA_VISIBLE_DEVICES=0
-( time timeout 1200 python -m pytest tests -m gpu -x -q ) > gpurun_out/pytest_gpu_1gpu.log 2>&1; tail -6 gpurun_out/pytest_gpu_1gpu.log
-timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2
-( time timeout 900 python bench.py ) > gpurun_out/bench_n1.json 2> gpurun_out/bench_n1.err; python -c "
-import json; d=json.loads(open('gpurun_out/bench_n1.json').read().strip().splitlines()[-1]); print(d['value'], d['roofline']['frac'], d['e2e']['value'], d['hbm_sustained']['value'], d['roofline_gemm']['achieved'], d['roofline_gemm']['classes']['uniform_philox']['ours_over_cublas'], d['probe_round'], d['clocks'])"; tail -3 gpurun_out/bench_n1.err
+tools/build/smid_probe > gpurun_out/smid_probe.txt 2>&1; head -3 gpurun_out/smid_probe.txt; grep -c "not one TPC" gpurun_out/smid_probe.txt; awk 'NR>2{print $2}' gpurun_out/smid_probe.txt | tr '\n' ' ' | head -c 600; echo
+export B200PROBE_LIB=$PWD/k3s-nvidia_b200/libb200probe_exp.so
+B200PROBE_GEMM_SMID_MAP=1 timeout 600 python -m pytest tests/test_gpu_gemm.py -m gpu -x -q -k "pair512-stg or headline" 2>&1 | tail -3
+GEMM_TUNE_QUICK=1 timeout 900 python tools/gemm_tune.py 2>&1 | tail -24

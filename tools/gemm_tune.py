@@ -21,7 +21,7 @@ Cm = torch.empty(M * N, dtype=torch.int16, device=dev)
 Cl = torch.empty(M, N, dtype=torch.bfloat16, device=dev)
 Ab, Bb = A.view(torch.bfloat16).view(M, K), B.view(torch.bfloat16).view(N, K)
 flop = 2.0 * M * N * K
-KNOBS = ["B200PROBE_GEMM_VARIANT", "B200PROBE_GEMM_GROUP_M", "B200PROBE_GEMM_POL_A", "B200PROBE_GEMM_POL_B", "B200PROBE_GEMM_POL_C", "B200PROBE_GEMM_PREFETCH", "B200PROBE_GEMM_EXPT", "B200PROBE_GEMM_EPI", "B200PROBE_GEMM_SKEW", "B200PROBE_GEMM_SMID_MAP"]
+KNOBS = ["B200PROBE_GEMM_VARIANT", "B200PROBE_GEMM_GROUP_M", "B200PROBE_GEMM_POL_A", "B200PROBE_GEMM_POL_B", "B200PROBE_GEMM_POL_C", "B200PROBE_GEMM_PREFETCH", "B200PROBE_GEMM_EXPT", "B200PROBE_GEMM_EPI", "B200PROBE_GEMM_SKEW"]
 
 
 def ours():
@@ -70,7 +70,7 @@ for cls, cname in ((1, "U(-1,1) Philox operands"), (0, "k/128 operands")):
     combos = [dict(v=3, g=4), dict(v=2, g=8), "cublas", dict(v=3, g=2), dict(v=3, g=8), dict(v=3, g=1), dict(v=3, g=16), dict(v=3, g=3), "cublas",
               dict(v=3, g=4, c=1), dict(v=3, g=4, a=2), dict(v=3, g=4, b=1), dict(v=3, g=4, a=2, b=1, c=1), dict(v=2, g=8), dict(v=3, g=4), "cublas"]
     if os.environ.get("GEMM_TUNE_QUICK"):
-        combos = [dict(v=3, g=4), "cublas", dict(v=3, g=4, m=1), dict(v=3, g=8, m=1), dict(v=3, g=2, m=1), dict(v=3, g=1, m=1), dict(v=3, g=16, m=1), "cublas", dict(v=3, g=4), dict(v=3, g=4, m=1), "cublas"]
+        combos = [dict(v=3, g=4), "cublas", dict(v=3, g=4, s=1), dict(v=3, g=4, s=2), dict(v=3, g=4, e=1), dict(v=3, g=8), "cublas", dict(v=2, g=8), dict(v=3, g=4, x=1), dict(v=3, g=4), "cublas"]
     if os.environ.get("GEMM_TUNE_QUICK") == "prefetch":
         combos = [dict(v=3, g=4), "cublas", dict(v=3, g=4, p=2), dict(v=3, g=4, p=4), dict(v=3, g=4, p=8), dict(v=3, g=4, p=16), "cublas", dict(v=3, g=4, p=32),
                   dict(v=3, g=8, p=8), dict(v=3, g=4), dict(v=3, g=4, p=8), "cublas"]
@@ -82,7 +82,7 @@ for cls, cname in ((1, "U(-1,1) Philox operands"), (0, "k/128 operands")):
         else:
             os.environ[KNOBS[0]] = str(kw["v"])
             os.environ[KNOBS[1]] = str(kw["g"])
-            for key, env in (("a", KNOBS[2]), ("b", KNOBS[3]), ("c", KNOBS[4]), ("p", KNOBS[5]), ("x", KNOBS[6]), ("e", KNOBS[7]), ("s", KNOBS[8]), ("m", KNOBS[9])):
+            for key, env in (("a", KNOBS[2]), ("b", KNOBS[3]), ("c", KNOBS[4]), ("p", KNOBS[5]), ("x", KNOBS[6]), ("e", KNOBS[7]), ("s", KNOBS[8])):
                 if key in kw:
                     os.environ[env] = str(kw[key])
             bu, su = burst(ours), sustained(ours)
@@ -90,7 +90,7 @@ for cls, cname in ((1, "U(-1,1) Philox operands"), (0, "k/128 operands")):
             torch.cuda.synchronize()
             same = bool((Cm.view(torch.bfloat16).view(M, N) == Cl).all().item())
             tile = "512x256" if kw["v"] == 3 else "256x256"
-            line = (f"ours {tile} band {kw['g']:>2}  A-pol {kw.get('a', 0)} B-pol {kw.get('b', 0)} C-pol {kw.get('c', 0)} prefetch {kw.get('p', 0):>2} expt {kw.get('x', 0)} epi {'tma' if kw.get('e') else 'stg'} skew {kw.get('s', 0)} smid-map {kw.get('m', 0)}  burst {bu:7.1f}   sustained {su:7.1f}"
+            line = (f"ours {tile} band {kw['g']:>2}  A-pol {kw.get('a', 0)} B-pol {kw.get('b', 0)} C-pol {kw.get('c', 0)} prefetch {kw.get('p', 0):>2} expt {kw.get('x', 0)} epi {'tma' if kw.get('e') else 'stg'} skew {kw.get('s', 0)}  burst {bu:7.1f}   sustained {su:7.1f}"
                     f"   C == cuBLAS: {same}")
         lines.append(line)
         print(line, flush=True)
