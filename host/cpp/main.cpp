@@ -51,8 +51,9 @@ static int hpack_decode_stdin() {
 // labels.py).  One record per line:
 //   hbm <gpu> <bytes> <mode 1|2|4> <gbs_median> <verified> <cache_resident>
 //   gemm <gpu> <tflops_median> <verified>
-//   passive <gpu> <links_total> <links_active> <fabric_state> <fabric_status> <fabric_health_mask>
+//   passive <gpu> <links_total> <links_active> <fabric_state> <fabric_status> <fabric_health_mask> [<active_mask>]
 //   a2a <G> <verified> <min_pair_gbs> <G egress> <G ingress> <G*G pair, row-major>
+//   a2ax <pair_source> <G ids>        (optional, after a2a: what the matrix holds and the NVML index of every position -> nvlink_localise)
 static int labels_from_stdin() {
     std::map<int, std::vector<b200probe_hbm_result_t>> hbm;
     std::map<int, b200probe_gemm_result_t> gemm;
@@ -60,6 +61,7 @@ static int labels_from_stdin() {
     bool have_a2a = false;
     b200probe_a2a_result_t rep;
     std::vector<double> pair;
+    std::vector<int> ids;
     memset(&rep, 0, sizeof(rep));
     std::string line;
     while (std::getline(std::cin, line)) {
@@ -82,6 +84,8 @@ static int labels_from_stdin() {
             int gpu; b200probe_nvlink_status_t st;
             memset(&st, 0, sizeof(st));
             in >> gpu >> st.links_total >> st.links_active >> st.fabric_state >> st.fabric_status >> st.fabric_health_mask;
+            unsigned mask = 0;
+            if (in >> mask) st.active_mask = mask;
             passive[gpu] = st;
         } else if (kind == "a2a") {
             in >> rep.g >> rep.verified >> rep.min_pair_gbs;
@@ -90,6 +94,10 @@ static int labels_from_stdin() {
             pair.assign((size_t)(rep.g * rep.g), 0.0);
             for (auto& v : pair) in >> v;
             have_a2a = true;
+        } else if (kind == "a2ax") {
+            in >> rep.pair_source;
+            ids.assign((size_t)rep.g, 0);
+            for (auto& v : ids) in >> v;
         }
     }
     labels::Thresholds th;
@@ -98,7 +106,10 @@ static int labels_from_stdin() {
     if (!hbm.empty()) merge(labels::hbm_labels(hbm, th));
     if (!gemm.empty()) merge(labels::gemm_labels(gemm, th));
     merge(labels::nvlink_passive_labels(passive));
-    if (have_a2a) merge(labels::nvlink_labels(rep, pair, th));
+    if (have_a2a) {
+        merge(labels::nvlink_labels(rep, pair, th, ids));
+        if (!ids.empty()) merge(labels::nvlink_localise(rep, pair, ids, passive));
+    }
     labels::gate_label(&l);
     fputs(labels::render(l).c_str(), stdout);
     return 0;

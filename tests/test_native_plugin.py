@@ -744,6 +744,69 @@ def test_label_rules_match_the_python_host_on_synthetic_probe_results():
         assert out == L.render(want), (trial, lines)
 
 
+def test_link_localisation_is_the_same_function_in_both_hosts():
+    """SURVEY.md §8f.3 twin check: random pair matrices (healthy, one cold endpoint, cold rows / columns, single cold pairs, ties)
+    joined with random passive link states give byte-identical label sets from labels.hpp and labels.py, for exchanges over a
+    SUBSET of the node's GPUs (positions != NVML indices)."""
+    import random
+    from types import SimpleNamespace as NS
+
+    from k3s_nvidia_b200 import _lib
+    from k3s_nvidia_b200 import labels as L
+
+    rng = random.Random(8763)
+    for trial in range(120):
+        n_node = rng.randint(2, 8)
+        ids = sorted(rng.sample(range(n_node), rng.randint(2, n_node)))          # the idle GPUs that took part, by NVML index
+        g = len(ids)
+        base = rng.choice([700.0, 705.5, 692.0])
+        pair = [[0.0 if i == j else base + rng.uniform(-4, 4) for j in range(g)] for i in range(g)]
+        kind = rng.random()
+        bad = rng.randrange(g)
+        if kind < 0.25:                                                          # one endpoint cold in both directions
+            for q in range(g):
+                if q != bad:
+                    pair[bad][q] = base * rng.uniform(0.5, 0.88)
+                    pair[q][bad] = base * rng.uniform(0.5, 0.88)
+        elif kind < 0.45:                                                        # cold row (egress) or column (ingress)
+            for q in range(g):
+                if q != bad:
+                    if kind < 0.35:
+                        pair[bad][q] = base * 0.8
+                    else:
+                        pair[q][bad] = base * 0.8
+        elif kind < 0.6:                                                         # a single cold pair, or two with equal values (tie-breaks)
+            i, j = rng.sample(range(g), 2)
+            pair[i][j] = 500.0
+            if rng.random() < 0.5:
+                pair[j][i] = 500.0
+        source = rng.choice([_lib.PAIR_STEPPED, _lib.PAIR_STEPPED, _lib.PAIR_ISOLATED, _lib.PAIR_SHARE])
+        passive, lines = {}, []
+        for idx in range(n_node):
+            total = 18
+            down = 0
+            if rng.random() < 0.25:
+                for link in rng.sample(range(18), rng.randint(1, 3)):
+                    down |= 1 << link
+            st = dict(links_total=total, links_active=total - bin(down).count("1"), active_mask=((1 << total) - 1) & ~down, fabric_state=3, fabric_status=0,
+                      fabric_health_mask=0)
+            passive[idx] = st
+            lines.append(f"passive {idx} {total} {st['links_active']} 3 0 0 {st['active_mask']}")
+        flat = [v for row in pair for v in row if v > 0]
+        egress = [sum(pair[i]) / (g - 1) for i in range(g)]
+        lines.append(f"a2a {g} 1 {min(flat)!r} " + " ".join(repr(x) for x in egress + egress + [v for row in pair for v in row]))
+        lines.append(f"a2ax {source} " + " ".join(str(i) for i in ids))
+        rep = NS(g=g, verified=1, egress_gbs=egress, ingress_gbs=egress, pair_gbs=pair, min_pair_gbs=min(flat), max_pair_gbs=max(flat), pair_source=source)
+        th = L.Thresholds()
+        want = {}
+        want.update(L.nvlink_passive_labels(passive))
+        want.update(L.nvlink_labels(rep, th, ids))
+        want.update(L.nvlink_localise(rep, ids, passive))
+        want.update(L.gate_label(want))
+        out = subprocess.run([BIN, "--labels-from-stdin"], input="\n".join(lines) + "\n", capture_output=True, text=True, check=True).stdout
+        assert out == L.render(want), (trial, kind, source, ids, lines[-2:], out, L.render(want))
+
+
 def test_sighup_reloads_the_config_document(both_hosts):
     """a rewritten config file + SIGHUP (what the chart's config-manager does [RECALLED]) -> new
     replica count advertised after a fresh Register; a document that does not parse keeps the running one.

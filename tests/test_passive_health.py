@@ -156,9 +156,17 @@ def test_close_waits_for_a_thread_blocked_in_the_event_wait(monkeypatch):
             out["ev"] = p.health_wait(400)
             out["dt"] = time.perf_counter() - t0
 
+        import ctypes as C
+
+        mock = C.CDLL(_oracle.MOCK_NVML)               # same handle the library dlopen()ed: its wait counter tells when the waiter is inside
+        before = mock.mock_nvml_wait_calls()
         th = threading.Thread(target=waiter)
         th.start()
-        time.sleep(0.08)
+        t_end = time.time() + 5
+        while mock.mock_nvml_wait_calls() == before and time.time() < t_end:
+            time.sleep(0.005)
+        assert mock.mock_nvml_wait_calls() > before, "the waiter never reached nvmlEventSetWait_v2"
+        time.sleep(0.02)
         t0 = time.perf_counter()
         p.health_close()                                    # must not return while the waiter is inside NVML
         closed_after = time.perf_counter() - t0
