@@ -7,6 +7,7 @@ import json
 import os
 import signal
 import subprocess
+import sys
 import time
 
 import grpc
@@ -805,6 +806,49 @@ def test_link_localisation_is_the_same_function_in_both_hosts():
         want.update(L.gate_label(want))
         out = subprocess.run([BIN, "--labels-from-stdin"], input="\n".join(lines) + "\n", capture_output=True, text=True, check=True).stdout
         assert out == L.render(want), (trial, kind, source, ids, lines[-2:], out, L.render(want))
+
+
+@pytest.mark.parametrize("host", ["native", "python"])
+def test_daemon_publishes_an_expiring_file_and_withdraws_it_on_sigterm(host, tmp_path, monkeypatch):
+    """The active-probe runner inside the daemon (both hosts): first round at start-up writes features.d/b200probe with the
+    expiry directive; SIGTERM wakes the runner out of its 600 s sleep at once (the native stop() could lose the
+    wake-up and block for the whole interval), the verdicts are withdrawn and the process exits."""
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("GPU present: the round would run the real probes")
+    monkeypatch.setenv("PYTHONPATH", ROOT + os.pathsep + os.environ.get("PYTHONPATH", ""))
+    d = str(tmp_path)
+    kubelet = FakeKubelet(d)
+    kubelet.start()
+    cfg = os.path.join(d, "config.yaml")
+    open(cfg, "w").write(VALUES.raw_configs["default"])
+    feat = os.path.join(d, "features.d")
+    cmd = [BIN] if host == "native" else [sys.executable, "-m", "k3s_nvidia_b200.plugin"]
+    env = dict(os.environ, MOCK_NVML_DEVICES="2")
+    log = open(os.path.join(d, "daemon.log"), "w")
+    proc = subprocess.Popen([*cmd, "--config-file", cfg, "--socket-dir", d, "--nvml-path", _oracle.MOCK_NVML, "--features-dir", feat,
+                             "--probe-interval", "600", "--watch-period", "0.05", "--health-timeout-ms", "5"], env=env, stderr=log)
+    try:
+        path = os.path.join(feat, "b200probe")
+        t_end = time.time() + 30
+        while not os.path.exists(path) and time.time() < t_end and proc.poll() is None:
+            time.sleep(0.05)
+        assert os.path.exists(path), open(os.path.join(d, "daemon.log")).read()[-2000:]
+        text = open(path).read()
+        assert text.startswith("# +expiry-time=") and "nvidia.com/b200probe.healthy=false" in text       # no CUDA here: probes fail, gate false
+        assert "nvidia.com/b200probe.gpu0.probe-state=probed" in text and "timestamp" not in text
+        assert kubelet.event.wait(30)
+        t0 = time.time()
+        proc.send_signal(signal.SIGTERM)
+        proc.wait(10)
+        assert time.time() - t0 < 5.0, "the runner did not wake up from its interval sleep"
+        assert not os.path.exists(path), "the feature file must be withdrawn on a clean stop"
+    finally:
+        if proc.poll() is None:
+            proc.kill()
+        log.close()
+        kubelet.stop()
 
 
 def test_sighup_reloads_the_config_document(both_hosts):
