@@ -844,6 +844,9 @@ def test_daemon_publishes_an_expiring_file_and_withdraws_it_on_sigterm(host, tmp
         proc.wait(10)
         assert time.time() - t0 < 5.0, "the runner did not wake up from its interval sleep"
         assert not os.path.exists(path), "the feature file must be withdrawn on a clean stop"
+        log.flush()
+        text = open(os.path.join(d, "daemon.log")).read()
+        assert "Sanitizer" not in text and "runtime error" not in text, text[-4000:]      # asan / tsan builds report on stderr
     finally:
         if proc.poll() is None:
             proc.kill()
@@ -1086,6 +1089,7 @@ def test_both_hosts_skip_a_busy_gpu_the_same_way(tmp_path, monkeypatch):
     out = subprocess.run([BIN, "--probe-once", "--features-dir", str(tmp_path / "native"), "--nvml-path", _oracle.MOCK_NVML], env=env,
                          capture_output=True, text=True, timeout=60)
     assert out.returncode == 0, out.stderr
+    assert "Sanitizer" not in out.stderr and "runtime error" not in out.stderr, out.stderr[-4000:]
     native = L.parse_feature_file(out.stdout)
     monkeypatch.setenv("MOCK_NVML_DEVICES", "2")
     monkeypatch.setenv("MOCK_NVML_BUSY", "1:1:0")
