@@ -8,6 +8,7 @@
 //   b200-device-plugin --check-config FILE          print the parsed configuration as JSON (parity tests)
 //   b200-device-plugin --check-values FILE          the same for the chart's values.yaml (gfd, runtimeClassName, config.map)
 //   b200-device-plugin --probe-once                 one active-probe round, labels on stdout
+//   b200-device-plugin --probe-rounds N             N rounds of one runner, labels after each (tests)
 #include <signal.h>
 
 #include <fstream>
@@ -183,6 +184,7 @@ int main(int argc, char** argv) {
     std::string features_dir = "/etc/kubernetes/node-feature-discovery/features.d";
     double probe_interval = getenv("B200PROBE_INTERVAL_S") ? atof(getenv("B200PROBE_INTERVAL_S")) : 600.0, watch_period = 1.0;
     bool active = true, probe_once = false, health = true;
+    int probe_rounds = 1;
     int health_timeout_ms = 5000;
     for (int i = 1; i < argc; ++i) {
         const std::string a = argv[i];
@@ -203,6 +205,7 @@ int main(int argc, char** argv) {
         else if (a == "--no-active-probe") active = false;
         else if (a == "--no-health") health = false;
         else if (a == "--probe-once") probe_once = true;
+        else if (a == "--probe-rounds") { val(&v); probe_once = true; probe_rounds = std::max(1, atoi(v.c_str())); }   // N rounds of ONE runner (tests: carry-over, calibration)
         else if (a == "--version") { printf("b200-device-plugin abi %d\n", b200probe_abi_version()); return 0; }
         else { fprintf(stderr, "unknown argument %s\n", a.c_str()); return 2; }
     }
@@ -211,7 +214,10 @@ int main(int argc, char** argv) {
     if (probe_once) {
         try {
             labels::ActiveProbeRunner runner(features_dir, 0);
-            fputs(labels::render(runner.run_once()).c_str(), stdout);
+            for (int r = 0; r < probe_rounds; ++r) {
+                if (probe_rounds > 1) printf("== round %d\n", r);
+                fputs(labels::render(runner.run_once()).c_str(), stdout);
+            }
             return 0;
         } catch (const std::exception& e) { plugin::logf("probe round failed: %s", e.what()); return 1; }
     }

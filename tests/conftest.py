@@ -21,6 +21,7 @@ def _built():
         os.path.join(ROOT, "k3s-nvidia_b200", "libb200probe.so"),
         os.path.join(ROOT, "oracle", "liboracle.so"),
         os.path.join(ROOT, "tests", "mock_nvml", "libnvidia-ml-mock.so"),
+        os.path.join(ROOT, "tests", "fake_probe", "libfakeprobe.so"),
         os.path.join(ROOT, "host", "cpp", "build", "b200-device-plugin"),
     ]
     if not all(os.path.exists(p) for p in need):

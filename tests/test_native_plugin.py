@@ -854,6 +854,65 @@ def test_daemon_publishes_an_expiring_file_and_withdraws_it_on_sigterm(host, tmp
         kubelet.stop()
 
 
+def test_scripted_probe_rounds_give_the_same_labels_in_both_hosts(tmp_path, monkeypatch):
+    """The whole policy of the active-probe runner, round by round, native host against Python host on the SAME script:
+    calibration on the first healthy round (and the stricter gate it implies afterwards), a busy GPU skipped with its last idle
+    verdict carried over and the exchange run over the idle subset, out-of-memory treated as inconclusive, cold cells named,
+    everything busy -> verdicts stand.  The native runner sees the script through an LD_PRELOAD interposer over the probe entry
+    points (tests/fake_probe), the Python runner through the duck-typed FakeProbe of test_labels.py; enumeration and passive
+    link state come from the mock NVML in both."""
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from k3s_nvidia_b200 import labels as L
+    from test_labels import FakeProbe
+
+    fake = os.path.join(ROOT, "tests", "fake_probe", "libfakeprobe.so")
+    rounds = [
+        dict(copy={0: 7000.0}),                                                        # gpu0's own figure is above the pool's: calibrated at 7000
+        dict(busy={1}, copy={0: 6100.0}),                                              # 6100 clears 0.9 x pool but not 0.9 x 7000; gpu1 keeps its verdict
+        dict(nomem={2}, pair={(3, 0): 600.0, (3, 1): 600.0}),                          # exchange over {0,1,3}: gpu3's egress row is cold
+        dict(pair={(0, 3): 500.0}),                                                    # all idle again: a single cold pair
+        dict(busy={0, 1, 2, 3}),                                                       # nothing measurable: every verdict stands
+    ]
+    preload = fake
+    if "asan" in os.path.basename(BIN):           # the ASan runtime must come first in the preload list
+        preload = subprocess.check_output(["/usr/bin/g++", "-print-file-name=libasan.so"], text=True).strip() + ":" + fake
+    env = dict(os.environ, MOCK_NVML_DEVICES="4", LD_PRELOAD=preload)
+    for r, sc in enumerate(rounds):
+        if sc.get("busy"):
+            env[f"FAKE_R{r}_BUSY"] = ",".join(str(i) for i in sorted(sc["busy"]))
+        if sc.get("nomem"):
+            env[f"FAKE_R{r}_NOMEM"] = ",".join(str(i) for i in sorted(sc["nomem"]))
+        if sc.get("copy"):
+            env[f"FAKE_R{r}_COPY"] = ",".join(f"{i}:{v}" for i, v in sc["copy"].items())
+        if sc.get("pair"):
+            env[f"FAKE_R{r}_PAIR"] = ",".join(f"{a}>{b}:{v}" for (a, b), v in sc["pair"].items())
+    out = subprocess.run([BIN, "--probe-rounds", str(len(rounds)), "--features-dir", str(tmp_path / "native"), "--nvml-path", _oracle.MOCK_NVML],
+                         env=env, capture_output=True, text=True, timeout=60)
+    assert out.returncode == 0, out.stderr
+    assert "Sanitizer" not in out.stderr and "runtime error" not in out.stderr, out.stderr[-3000:]
+    native = [L.parse_feature_file(chunk.split("\n", 1)[1]) for chunk in out.stdout.split("== round ")[1:]]
+    assert len(native) == len(rounds)
+
+    fp = FakeProbe(n=4)
+    runner = L.ActiveProbeRunner(fp, features_dir=str(tmp_path / "py"), interval_s=3600)
+    for r, sc in enumerate(rounds):
+        fp.busy, fp.nomem = set(sc.get("busy", ())), set(sc.get("nomem", ()))
+        fp.copy_gbs = {i: 6600.0 for i in range(4)}
+        fp.copy_gbs.update(sc.get("copy", {}))
+        fp.pair_override = dict(sc.get("pair", {}))
+        py = runner.run_once()
+        assert native[r] == py, (r, sorted(set(native[r].items()) ^ set(py.items())))
+    P = "nvidia.com/b200probe."
+    assert native[0][P + "healthy"] == "true"
+    assert native[1][P + "gpu0.hbm-healthy"] == "false" and native[1][P + "gpu1.probe-state"] == "busy" and native[1][P + "gpu1.hbm-copy-gbs"] == "6600"
+    assert native[2][P + "gpu2.probe-state"] == "no-memory" and native[2][P + "nvlink-suspect"] == "gpu3" and native[2][P + "nvlink-suspect-evidence"] == "egress-cold"
+    assert native[3][P + "nvlink-cold-cell"] == "gpu0-to-gpu3" and native[3][P + "nvlink-suspect-evidence"] == "pair-only"
+    assert native[4] == {**native[3], **{P + f"gpu{i}.probe-state": "busy" for i in range(4)}}
+
+
 def test_sighup_reloads_the_config_document(both_hosts):
     """a rewritten config file + SIGHUP (what the chart's config-manager does [RECALLED]) -> new
     replica count advertised after a fresh Register; a document that does not parse keeps the running one.
