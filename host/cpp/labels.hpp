@@ -117,6 +117,8 @@ inline Labels nvlink_labels(const b200probe_a2a_result_t& rep, const std::vector
     bool ok = rep.verified != 0;
     const double min_gbs = th.nvlink_min_gbs > 0 ? th.nvlink_min_gbs : (G <= 2 ? 0.97 * kNvlinkHealthyPair : 0.96 * kNvlinkHealthyBox);
     double min_egress = 1e300;
+    const char* pl = getenv("B200PROBE_PAIR_LABELS");                 // "0": no per-pair labels (the summary and the localisation stay)
+    const bool pair_labels = !(pl && strcmp(pl, "0") == 0);
     for (int pos = 0; pos < G; ++pos) {
         const int g = ids[(size_t)pos];
         out[key(g, "nvlink-egress-gbs")] = rint_str(rep.egress_gbs[pos]);
@@ -126,7 +128,7 @@ inline Labels nvlink_labels(const b200probe_a2a_result_t& rep, const std::vector
         ok = ok && good;
         min_egress = std::min(min_egress, rep.egress_gbs[pos]);
         for (int q = 0; q < G; ++q)
-            if (q != pos && pair_gbs[(size_t)(pos * G + q)] > 0)
+            if (pair_labels && q != pos && pair_gbs[(size_t)(pos * G + q)] > 0)
                 out[key(g, ("nvlink-to-gpu" + std::to_string(ids[(size_t)q]) + "-gbs").c_str())] = rint_str(pair_gbs[(size_t)(pos * G + q)]);
     }
     out[key("nvlink-min-pair-gbs")] = rint_str(rep.min_pair_gbs);

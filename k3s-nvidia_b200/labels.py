@@ -126,6 +126,9 @@ def nvlink_labels(rep, th: Thresholds, ids: Optional[List[int]] = None) -> Dict[
     ok = rep.verified != 0
     ids = list(ids) if ids is not None else list(range(rep.g))
     min_gbs = th.nvlink_min_gbs or (0.97 * NVLINK_HEALTHY_GBS if rep.g <= 2 else 0.96 * NVLINK_HEALTHY_GBS_BOX)
+    # G*(G-1) per-pair labels are what BASELINE config 3 asks for ("per-link GB/s surfaced as NFD node labels"); a cluster that
+    # only gates on the summary can switch them off (B200PROBE_PAIR_LABELS=0: 56 labels fewer on an 8-GPU node)
+    pair_labels = os.environ.get("B200PROBE_PAIR_LABELS", "1") != "0"
     for pos in range(rep.g):
         g = ids[pos]
         out[f"{PREFIX}gpu{g}.nvlink-egress-gbs"] = str(int(round(rep.egress_gbs[pos])))
@@ -134,7 +137,7 @@ def nvlink_labels(rep, th: Thresholds, ids: Optional[List[int]] = None) -> Dict[
         out[f"{PREFIX}gpu{g}.nvlink-healthy"] = _b(good and rep.verified != 0)
         ok = ok and good
         for q in range(rep.g):
-            if q != pos and rep.pair_gbs[pos][q] > 0:
+            if pair_labels and q != pos and rep.pair_gbs[pos][q] > 0:
                 out[f"{PREFIX}gpu{g}.nvlink-to-gpu{ids[q]}-gbs"] = str(int(round(rep.pair_gbs[pos][q])))
     out[f"{PREFIX}nvlink-min-pair-gbs"] = str(int(round(rep.min_pair_gbs)))
     out[f"{PREFIX}nvlink-egress-pct-of-nominal"] = str(int(round(100.0 * min(rep.egress_gbs[: rep.g]) / NVLINK_NOMINAL_GBS)))

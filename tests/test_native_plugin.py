@@ -911,6 +911,16 @@ def test_scripted_probe_rounds_give_the_same_labels_in_both_hosts(tmp_path, monk
     assert native[2][P + "gpu2.probe-state"] == "no-memory" and native[2][P + "nvlink-suspect"] == "gpu3" and native[2][P + "nvlink-suspect-evidence"] == "egress-cold"
     assert native[3][P + "nvlink-cold-cell"] == "gpu0-to-gpu3" and native[3][P + "nvlink-suspect-evidence"] == "pair-only"
     assert native[4] == {**native[3], **{P + f"gpu{i}.probe-state": "busy" for i in range(4)}}
+    # the per-pair labels can be switched off in both hosts; summary and localisation stay
+    env["B200PROBE_PAIR_LABELS"] = "0"
+    monkeypatch.setenv("B200PROBE_PAIR_LABELS", "0")
+    out = subprocess.run([BIN, "--probe-rounds", "1", "--features-dir", str(tmp_path / "native2"), "--nvml-path", _oracle.MOCK_NVML],
+                         env=env, capture_output=True, text=True, timeout=60)
+    lean = L.parse_feature_file(out.stdout)
+    fp2 = FakeProbe(n=4)
+    fp2.copy_gbs[0] = 7000.0
+    assert lean == L.ActiveProbeRunner(fp2, features_dir=str(tmp_path / "py2"), interval_s=3600).run_once()
+    assert not [k for k in lean if "nvlink-to-gpu" in k] and lean[P + "nvlink-cold-cell"] == "none" and len(native[0]) - len(lean) == 12
 
 
 def test_sighup_reloads_the_config_document(both_hosts):
