@@ -357,7 +357,12 @@ def run_ours(args):
         p.lib.b200probe_hbm_release(local_rank)
 
         peaks, peak_src = measured_peaks()
-        gemm = None if args.no_gemm else gemm_leg(torch, p, local_rank, nvml_index, peaks, ClockSampler(nvml_index))
+        gemm = None
+        if not args.no_gemm:
+            try:                                   # a side leg must never cost the line: its failure is reported inside it
+                gemm = gemm_leg(torch, p, local_rank, nvml_index, peaks, ClockSampler(nvml_index))
+            except Exception as e:  # noqa: BLE001
+                gemm = {"bound": "tensor", "error": str(e)[:300]}
         probe_round = None if args.no_probe_round else probe_round_leg(p)
         traffic = None
         try:
