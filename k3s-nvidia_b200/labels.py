@@ -21,7 +21,9 @@ the tenants, so a round first asks NVML who is on each device (b200probe_device_
 ``gpu<i>.probe-state=busy``, the last idle verdict of that GPU is carried over unchanged, and nothing of ours
 touches it (B200PROBE_IGNORE_TENANTS=1 turns the check off: benches and tests, where the caller itself is the
 tenant).  A failed device allocation (B200PROBE_ENOMEM) is treated the same way (``no-memory``), never as
-unhealthy.  A GPU that has never been measured has no verdict and the gate label is absent (selectors on
+unhealthy.  (NVML's utilisation figure averages over its last sample period, up to a second: with a probe interval of that order a
+round would see the PREVIOUS round's own load and skip — the interval is meant to be minutes, the default is 600 s.)  A GPU that has
+never been measured has no verdict and the gate label is absent (selectors on
 ``...healthy=true`` do not match: unknown is not healthy).  After every round all probe arenas are released.
 
 Staleness.  The file starts with NFD's ``# +expiry-time=`` directive (now + 2 rounds), so a hung or killed daemon
